@@ -1,0 +1,288 @@
+// tcgen05 + TMA GEMM / multi-tap 1-D convolution kernel for sm_100a.
+//
+//   C[b, r, n] = sum_{tap} sum_{k} A[b, r + off0 + tap*tap_stride, k] * W[n, tap*K + k]
+//
+// A is a K-major activation tensor [batch, rows, K] (bf16, or fp32 consumed as tf32); rows outside
+// [0, rows) read as zero through TMA out-of-bounds fill, which is what gives every sample of a
+// batch its own zero halo for the k=3 / k=7 convolutions and the transposed-conv polyphase form.
+// W is a K-major weight matrix [N, taps*K].  One CTA computes one 128 x BN output tile (optionally one
+// K-split of it): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma
+// issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> fused epilogue -> global).
+//
+// Replaces, on the reference path: F.linear / Conv1d(k=1,3) in hifi_foley.py:216-331,364-390,
+// mlp_layers.py:104-149, and the DAC decoder convs in dac.py:28-44,98-149.
+#pragma once
+#include "ptx.cuh"
+
+namespace foley {
+
+enum EpiMode : int {
+    EPI_BF16 = 0,    // out(bf16) = act(bf16r(acc + bias))
+    EPI_SWIGLU = 1,  // columns hold (w1_j, w3_j) pairs: out(bf16)[j] = bf16r(bf16r(silu(bf16r(a))) * bf16r(b))
+    EPI_F32 = 2,     // out(fp32)[split] = acc     (raw partial sums; consumer applies bias/gate)
+    EPI_DAC = 3,     // fp32 conv epilogue: y = acc + bias (+resid); out = y; out2 = snake(y) / tanh(y)
+};
+enum ActMode : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU_TANH = 2, ACT_TANH = 3 };
+
+struct GemmEpi {
+    int mode = EPI_BF16;
+    int act = ACT_NONE;
+    void* out = nullptr;            // primary output
+    long long ldo = 0;              // elements between output rows
+    long long out_batch_stride = 0; // elements between samples
+    long long split_stride = 0;     // EPI_F32: elements between K-split partials
+    const void* bias = nullptr;     // bf16[N] (DiT) or fp32[ch_mod] (DAC); may be null
+    // --- EPI_DAC only
+    void* out2 = nullptr;           // snake(y) with alpha (next conv's input); may be null
+    const float* resid = nullptr;   // residual input, same indexing as out; may be null
+    const float* alpha = nullptr;   // snake alpha per channel for out2
+    int ch_mod = 0;                 // channel = col % ch_mod (bias/alpha index); 0 -> col
+    long long flat_lo = 0, flat_hi = 0;  // if flat_hi > flat_lo: store only when flat_lo <= r*ldo+col < flat_hi
+};
+
+struct GemmArgs {
+    int rows;        // valid rows per sample
+    int n;           // output columns (N)
+    int kb_per_tap;  // K / BLOCK_K
+    int taps;
+    int tap_off0;    // A row offset of tap 0
+    int tap_stride;  // A row offset increment per tap
+    int splits;      // K splits (gridDim.z); the taps*kb_per_tap k-blocks are divided evenly
+    int dbg_stop;    // bring-up aid: 1 = setup only, 2 = TMA only, 3 = TMA+MMA, 0 = full kernel
+    GemmEpi epi;
+};
+
+template <int BN, bool kTF32>
+struct GemmCfg {
+    static constexpr int BM = 128;
+    static constexpr int BK_BYTES = 128;                      // one swizzle-128B row
+    static constexpr int BK = kTF32 ? 32 : 64;                // elements per k-block
+    static constexpr int UMMA_K = kTF32 ? 8 : 16;             // 32 bytes per instruction
+    static constexpr int A_BYTES = BM * BK_BYTES;             // 16 KB
+    static constexpr int B_BYTES = BN * BK_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int THREADS = 192;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    switch (act) {
+        case ACT_SILU: return x / (1.0f + expf(-x));
+        case ACT_GELU_TANH: return gelu_tanh_f(x);
+        case ACT_TANH: return tanhf(x);
+        default: return x;
+    }
+}
+
+template <int BN, bool kTF32>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                    const GemmArgs g) {
+    using Cfg = GemmCfg<BN, kTF32>;
+    extern __shared__ uint8_t smem_raw[];
+    // swizzle-128B tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + Cfg::STAGES * Cfg::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + Cfg::STAGES;
+    uint64_t* tmem_full_bar = bars + 2 * Cfg::STAGES;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int m_tiles = (g.rows + Cfg::BM - 1) / Cfg::BM;
+    const int batch = blockIdx.y / m_tiles;
+    const int m0 = (blockIdx.y % m_tiles) * Cfg::BM;
+    const int split = blockIdx.z;
+
+    const int kb_total = g.taps * g.kb_per_tap;
+    const int kb_begin = static_cast<int>((static_cast<long long>(kb_total) * split) / g.splits);
+    const int kb_end = static_cast<int>((static_cast<long long>(kb_total) * (split + 1)) / g.splits);
+    const int num_kb = kb_end - kb_begin;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_b);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    } else if (warp == 1) {
+        tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (g.dbg_stop == 1) {
+        // setup / teardown only
+    } else if (warp == 0) {
+        // ------------------------------------------------------------- TMA producer
+        if (lane == 0) {
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % Cfg::STAGES;
+                const uint32_t ph = (i / Cfg::STAGES) & 1;
+                if (!mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + i)) break;
+                const int kb = kb_begin + i;
+                const int tap = kb / g.kb_per_tap;
+                const int kcol = (kb - tap * g.kb_per_tap) * Cfg::BK;
+                mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                tma_load_3d(smem_a + s * Cfg::A_BYTES, &tm_a, &full_bar[s], kcol,
+                            m0 + g.tap_off0 + tap * g.tap_stride, batch);
+                tma_load_3d(smem_b + s * Cfg::B_BYTES, &tm_b, &full_bar[s], kb * Cfg::BK, n0, 0);  // rank-3 map, batch 0
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------- MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, Cfg::BM, BN);
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % Cfg::STAGES;
+                const uint32_t ph = (i / Cfg::STAGES) & 1;
+                if (!mbar_wait(&full_bar[s], ph, 0x200 + i)) break;
+                tc_fence_after();
+                if (g.dbg_stop == 2) { mbar_arrive(&empty_bar[s]); continue; }
+                const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + s * Cfg::A_BYTES));
+                const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::B_BYTES));
+#pragma unroll
+                for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; ++k) {
+                    // advance 32 bytes (= 2 x 16 B units) along K inside the swizzle atom
+                    if constexpr (kTF32)
+                        umma_tf32(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0);
+                    else
+                        umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+            }
+            if (g.dbg_stop == 2) mbar_arrive(tmem_full_bar);
+            else umma_commit(tmem_full_bar);  // accumulator complete
+        }
+    } else {
+        // ------------------------------------------------------------- epilogue warps (2..5)
+        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int r = m0 + q * 32 + lane;    // output row within the sample
+        const bool acc_ok = mbar_wait(tmem_full_bar, 0, 0x300);
+        tc_fence_after();
+        const GemmEpi& e = g.epi;
+        const bool row_ok = r < g.rows;
+        const long long row_off = static_cast<long long>(batch) * e.out_batch_stride +
+                                  static_cast<long long>(r) * e.ldo;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN && acc_ok && g.dbg_stop == 0; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+            tmem_ld_wait();
+            const int col = n0 + c0;
+            if (!row_ok || col >= g.n || num_kb <= 0) continue;
+            if (e.mode == EPI_BF16) {
+                const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(e.bias);
+                __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out) + row_off + col;
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
+                    if (bias) {
+                        a0 += __bfloat162float(bias[col + j]);
+                        a1 += __bfloat162float(bias[col + j + 1]);
+                    }
+                    if (e.act != ACT_NONE) {
+                        a0 = apply_act(bf16_round(a0), e.act);
+                        a1 = apply_act(bf16_round(a1), e.act);
+                    }
+                    packed[j >> 1] = pack_bf16x2(a0, a1);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(out);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            } else if (e.mode == EPI_SWIGLU) {
+                __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out) + row_off + (col >> 1);
+                uint32_t packed[8];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float g0 = bf16_round(__uint_as_float(v[j])), u0 = bf16_round(__uint_as_float(v[j + 1]));
+                    float g1 = bf16_round(__uint_as_float(v[j + 2])), u1 = bf16_round(__uint_as_float(v[j + 3]));
+                    float s0 = bf16_round(g0 / (1.0f + expf(-g0))) * u0;
+                    float s1 = bf16_round(g1 / (1.0f + expf(-g1))) * u1;
+                    packed[j >> 2] = pack_bf16x2(s0, s1);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(out);
+                dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            } else if (e.mode == EPI_F32) {
+                float* out = reinterpret_cast<float*>(e.out) + static_cast<long long>(split) * e.split_stride +
+                             row_off + col;
+                float4* dst = reinterpret_cast<float4*>(out);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            } else {  // EPI_DAC
+                const float* bias = reinterpret_cast<const float*>(e.bias);
+                const long long flat0 = static_cast<long long>(r) * e.ldo + col;
+                const bool windowed = e.flat_hi > e.flat_lo;
+                float* out = e.out ? reinterpret_cast<float*>(e.out) + row_off + col : nullptr;
+                float* out2 = e.out2 ? reinterpret_cast<float*>(e.out2) + row_off + col : nullptr;
+                const float* res = e.resid ? e.resid + row_off + col : nullptr;
+                const bool full_ok = !windowed || (flat0 >= e.flat_lo && flat0 + 32 <= e.flat_hi);
+                const bool any_ok = !windowed || (flat0 + 32 > e.flat_lo && flat0 < e.flat_hi);
+                if (!any_ok) continue;
+                float y[32], z[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int ch = e.ch_mod ? (col + j) % e.ch_mod : (col + j);
+                    float a = __uint_as_float(v[j]);
+                    if (bias) a += bias[ch];
+                    if (res && (full_ok || (flat0 + j >= e.flat_lo && flat0 + j < e.flat_hi))) a += res[j];
+                    y[j] = a;
+                    if (e.act == ACT_TANH) {
+                        z[j] = tanhf(a);
+                    } else if (e.alpha) {
+                        const float al = e.alpha[ch];
+                        const float sn = sinf(al * a);
+                        z[j] = a + (1.0f / (al + 1e-9f)) * sn * sn;
+                    } else {
+                        z[j] = a;
+                    }
+                }
+                if (full_ok) {
+                    if (out) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            reinterpret_cast<float4*>(out)[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                    }
+                    if (out2) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            reinterpret_cast<float4*>(out2)[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (flat0 + j >= e.flat_lo && flat0 + j < e.flat_hi) {
+                            if (out) out[j] = y[j];
+                            if (out2) out2[j] = z[j];
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace foley

@@ -1,0 +1,146 @@
+// Host side of the tcgen05 GEMM: TMA descriptor encoding (driver entry point fetched through the
+// runtime so the library has no link-time dependency on libcuda) and the launcher.
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "gemm.cuh"
+
+namespace foley {
+
+using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                     CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+enum DType : int { DT_BF16 = 0, DT_F32 = 1 };
+
+// A K-major operand view: element (b, r, k) lives at ptr + b*batch_stride + r*ld + k (elements).
+struct Operand {
+    const void* ptr = nullptr;
+    int dtype = DT_BF16;
+    long long k = 0;             // contiguous extent
+    long long rows = 0;
+    long long batch = 1;
+    long long ld = 0;            // elements between rows
+    long long batch_stride = 0;  // elements between samples
+};
+
+inline bool encode_operand_map(CUtensorMap* out, const Operand& t, int box_rows, std::string* err) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) { if (err) *err = "cuTensorMapEncodeTiled entry point unavailable"; return false; }
+    const int esz = t.dtype == DT_BF16 ? 2 : 4;
+    const cuuint32_t box_k = 128 / esz;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(t.k), static_cast<cuuint64_t>(t.rows),
+                          static_cast<cuuint64_t>(t.batch > 0 ? t.batch : 1)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(t.ld) * esz,
+                             static_cast<cuuint64_t>(t.batch > 1 ? t.batch_stride : t.ld * t.rows) * esz};
+    if (strides[1] == 0) strides[1] = strides[0];
+    cuuint32_t box[3] = {box_k, static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if ((reinterpret_cast<uintptr_t>(t.ptr) & 15) || (strides[0] & 15) || (strides[1] & 15)) {
+        if (err) *err = "TMA operand must be 16-byte aligned (pointer and strides)";
+        return false;
+    }
+    CUresult r = enc(out, t.dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
+                     3, const_cast<void*>(t.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): k=%lld rows=%lld batch=%lld ld=%lld bs=%lld",
+                     static_cast<int>(r), t.k, t.rows, t.batch, t.ld, t.batch_stride);
+            *err = buf;
+        }
+        return false;
+    }
+    return true;
+}
+
+struct GemmLaunch {
+    Operand a;                 // activations [batch, rows, K]
+    const void* w = nullptr;   // weights [N, taps*K], K-major, same dtype as a
+    long long n = 0;
+    int taps = 1, tap_off0 = 0, tap_stride = 1;
+    int splits = 1;
+    int bn = 128;              // tile width: 64, 128 or 256
+    int dbg_stop = 0;
+    GemmEpi epi;
+};
+
+template <int BN, bool kTF32>
+inline cudaError_t launch_gemm_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& args,
+                                    dim3 grid, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, kTF32>;
+    auto kern = gemm_tcgen05_kernel<BN, kTF32>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, args);
+    return cudaGetLastError();
+}
+
+inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* err) {
+    const bool tf32 = L.a.dtype == DT_F32;
+    const int bk = tf32 ? 32 : 64;
+    if (L.a.k % bk != 0) { if (err) *err = "GEMM K must be a multiple of the 128-byte k-block"; return false; }
+    if (L.n % 16 != 0) { if (err) *err = "GEMM N must be a multiple of 16"; return false; }
+    CUtensorMap ma, mb;
+    if (!encode_operand_map(&ma, L.a, 128, err)) return false;
+    Operand wb;
+    wb.ptr = L.w; wb.dtype = L.a.dtype; wb.k = L.a.k * L.taps; wb.rows = L.n; wb.batch = 1;
+    wb.ld = wb.k; wb.batch_stride = wb.k * wb.rows;
+    if (!encode_operand_map(&mb, wb, L.bn, err)) return false;
+
+    GemmArgs args;
+    args.rows = static_cast<int>(L.a.rows);
+    args.n = static_cast<int>(L.n);
+    args.kb_per_tap = static_cast<int>(L.a.k / bk);
+    args.taps = L.taps;
+    args.tap_off0 = L.tap_off0;
+    args.tap_stride = L.tap_stride;
+    args.splits = L.splits < 1 ? 1 : L.splits;
+    args.epi = L.epi;
+    args.dbg_stop = L.dbg_stop;
+    const int m_tiles = static_cast<int>((L.a.rows + 127) / 128);
+    dim3 grid(static_cast<unsigned>((L.n + L.bn - 1) / L.bn),
+              static_cast<unsigned>(m_tiles * (L.a.batch > 0 ? L.a.batch : 1)), static_cast<unsigned>(args.splits));
+    cudaError_t e = cudaSuccess;
+    if (!tf32) {
+        if (L.bn == 64) e = launch_gemm_inst<64, false>(ma, mb, args, grid, stream);
+        else if (L.bn == 128) e = launch_gemm_inst<128, false>(ma, mb, args, grid, stream);
+        else if (L.bn == 256) e = launch_gemm_inst<256, false>(ma, mb, args, grid, stream);
+        else { if (err) *err = "unsupported BN"; return false; }
+    } else {
+        if (L.bn == 64) e = launch_gemm_inst<64, true>(ma, mb, args, grid, stream);
+        else if (L.bn == 128) e = launch_gemm_inst<128, true>(ma, mb, args, grid, stream);
+        else if (L.bn == 256) e = launch_gemm_inst<256, true>(ma, mb, args, grid, stream);
+        else { if (err) *err = "unsupported BN"; return false; }
+    }
+    if (e != cudaSuccess) {
+        if (err) *err = std::string("GEMM launch failed: ") + cudaGetErrorString(e);
+        return false;
+    }
+    return true;
+}
+
+}  // namespace foley

@@ -1,0 +1,134 @@
+/*
+ * foley_b200.h — C ABI of libfoley_b200.so, the B200 (sm_100a) denoising engine that replaces the
+ * hot path of phazei/ComfyUI-HunyuanVideo-Foley behind its ComfyUI node surface.
+ *
+ * Every entry point returns a foley_status (0 = OK); no exceptions cross the boundary.  All tensor
+ * arguments are plain pointers + sizes.  Unless stated otherwise pointers are DEVICE pointers owned
+ * by the caller, and work is enqueued on the cudaStream_t passed as `stream` (void*; NULL = default
+ * stream).  Reference citations are relative to the reference repository root.
+ *
+ * Path replaced:
+ *   utils.py:125-258           denoise_process_with_generator      -> foley_denoise
+ *   hifi_foley.py:707-924      HunyuanVideoFoley.forward           -> foley_dit_forward
+ *   dac.py:280-303             DAC.decode                          -> foley_dac_decode
+ *   nodes.py:85-104, utils.py:61-87  state-dict loading            -> foley_engine_load_tensor
+ */
+#ifndef FOLEY_B200_H_
+#define FOLEY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int foley_status;
+enum {
+    FOLEY_OK = 0,
+    FOLEY_ERR_INVALID = 1,   /* bad argument / shape (reference raises RuntimeError / AssertionError) */
+    FOLEY_ERR_MISSING = 2,   /* weight missing at finalize (reference: load_state_dict(strict) error) */
+    FOLEY_ERR_CUDA = 3,      /* CUDA runtime / driver error, see foley_last_error */
+    FOLEY_ERR_STATE = 4,     /* call order violated (e.g. forward before conditions are set) */
+    FOLEY_ERR_UNSUPPORTED = 5
+};
+
+enum { FOLEY_DT_BF16 = 0, FOLEY_DT_F32 = 1, FOLEY_DT_F16 = 2 };
+
+/* Hyper-parameters of configs/hunyuanvideo-foley-{xl,xxl}.yaml (model_config.model_kwargs) that the
+ * hot path reads (hifi_foley.py:403-450), plus the torch semantics knobs the reference inherits. */
+typedef struct foley_config {
+    int32_t hidden_size;          /* 1536 (xxl) / 1408 (xl) */
+    int32_t num_heads;            /* 12 / 11; head_dim must be 128 */
+    int32_t depth_triple_blocks;  /* 18 / 12 */
+    int32_t depth_single_blocks;  /* 36 / 24 */
+    int32_t mlp_hidden_triple;    /* int(hidden*mlp_ratio) = 6144 / 5632 */
+    int32_t mlp_hidden_single;    /* ConvMLP hidden, 4096 / 3840 (mlp_layers.py:133-134) */
+    int32_t sync_hidden;          /* sync_in ConvMLP hidden (hifi_foley.py:482) */
+    int32_t latent_dim;           /* audio_vae_latent_dim = 128 */
+    int32_t clip_dim;             /* 768 */
+    int32_t sync_dim;             /* 768 */
+    int32_t text_dim;             /* condition_dim = 768 */
+    int32_t freq_dim;             /* TimestepEmbedder frequency_embedding_size = 256 */
+    float   rope_theta;           /* 10000 */
+    float   single_rms_eps;       /* eps torch's nn.RMSNorm(eps=None) uses for the model dtype */
+    int32_t max_batch;            /* largest number of variations per call (per GPU) */
+    int32_t max_seconds;          /* largest clip duration the buffers are sized for (node cap: 60) */
+    int32_t with_dac;             /* 1: allocate the DAC-VAE decoder too */
+} foley_config;
+
+typedef struct foley_engine foley_engine;
+
+/* Thread-local description of the last error returned by any call on this thread. */
+const char* foley_last_error(void);
+/* Library / build identification, e.g. "foley_b200 0.1 sm_100a". */
+const char* foley_version(void);
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+foley_status foley_engine_create(const foley_config* cfg, int device, foley_engine** out);
+void         foley_engine_destroy(foley_engine* e);
+
+/* ---- weights (nodes.py:85-104 load_state_dict; utils.py:61-87 load_dac_any) ------------------
+ * `name` is the reference state-dict key, e.g. "triple_blocks.3.audio_self_attn_qkv.weight",
+ * "single_blocks.7.linear2.w1.weight" ([4096,1536,3]) or, for the DAC-VAE,
+ * "dac.decoder.model.1.block.1.parametrizations.weight.original0".  `data` is a HOST pointer to a
+ * contiguous tensor of `dtype` with `ndim` dims `shape`.  The engine converts / repacks into its own
+ * device layout (conv k=3 -> tap-major GEMM rows, single-block QKV (H D K)->(K H D), SwiGLU w1/w3
+ * interleave, weight-norm folding).  Unknown names that belong to unused reference modules
+ * (DAC encoder, final_layer.adaLN_modulation, ...) are accepted and ignored, like strict=False. */
+foley_status foley_engine_load_tensor(foley_engine* e, const char* name, const void* data,
+                                      const int64_t* shape, int32_t ndim, int32_t dtype);
+/* Verifies that every tensor the hot path needs was provided; folds weight norm. */
+foley_status foley_engine_finalize(foley_engine* e);
+
+/* ---- conditions (utils.py:158-199; hifi_foley.py:744-770 step-invariant part) ----------------
+ * clip [n_cond, Lv, clip_dim], sync [n_cond, S, sync_dim], text [n_cond, T, text_dim], bf16 or f32,
+ * DEVICE pointers.  n_cond is 2 with CFG (row 0 = unconditional, row 1 = conditional, the order
+ * of torch.cat([uncond, cond]) in utils.py:192-199) or 1 without.  All variations of a batch share
+ * them (utils.py:159-162 `.repeat`).  `batch` variations x n_cond rows form the fused CFG batch.
+ * L = number of audio latent frames (= int(duration * 50)). */
+foley_status foley_set_conditions(foley_engine* e, const void* clip, const void* sync, const void* text,
+                                  int32_t dtype, int32_t n_cond, int32_t Lv, int32_t S, int32_t T,
+                                  int32_t L, int32_t batch, void* stream);
+
+/* ---- one velocity prediction (hifi_foley.py:707-924) ------------------------------------------
+ * x: [batch*n_cond, latent_dim, L] f32 (rows ordered like the reference's CFG batch: all uncond
+ * samples first), t: n_t host floats (timesteps in [0,1000]); n_t is 1 (shared) or batch*n_cond.
+ * out: [batch*n_cond, latent_dim, L] f32 holding the bf16-rounded model output. */
+foley_status foley_dit_forward(foley_engine* e, const float* x, const float* t, int32_t n_t, float* out,
+                               void* stream);
+
+/* ---- the whole Euler loop (utils.py:203-247 + scheduling_flow_match_discrete.py:210-297) ------
+ * latents: [batch, latent_dim, L] f32, in: initial noise, out: final latents.  sigmas: n_steps+1
+ * host floats (torch.linspace(1,0,n_steps+1) for shift=1).  guidance: CFG scale (used when
+ * n_cond==2).  progress(step, user) is called on the host after each step is enqueued-and-finished
+ * when non-NULL (ComfyUI ProgressBar.update, utils.py:247); NULL keeps the loop fully asynchronous. */
+typedef void (*foley_progress_fn)(int32_t step, void* user);
+foley_status foley_denoise(foley_engine* e, float* latents, const float* sigmas, int32_t n_steps,
+                           float guidance, foley_progress_fn progress, void* user, void* stream);
+
+/* ---- DAC-VAE decode (dac.py:280-303) ----------------------------------------------------------
+ * z: [batch, latent_dim, L] f32 -> wav: [batch, 1, L*hop] f32 (hop = 960). */
+foley_status foley_dac_decode(foley_engine* e, const float* z, int32_t batch, int32_t L, float* wav,
+                              void* stream);
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+/* Number of kernel launches the engine issued (graph-replayed launches included) since create. */
+int64_t      foley_launch_count(const foley_engine* e);
+/* Copies an internal activation buffer to `dst` (f32) for per-block parity tests; `what` names it
+ * (e.g. "audio", "v_cond", "vec"); returns the element count via n_out. */
+foley_status foley_debug_read(foley_engine* e, const char* what, float* dst, int64_t cap, int64_t* n_out);
+
+/* ---- low-level kernels exported for unit tests and micro-benchmarks --------------------------- */
+/* C[b,r,n] = sum_tap sum_k A[b, r+off0+tap*stride, k] * W[n, tap*K+k]; dtype bf16 -> tcgen05 kind::f16,
+ * f32 -> kind::tf32.  mode: 0 bf16 out (+bias,+act), 1 SwiGLU pairs, 2 f32 partials (splits).  */
+foley_status foley_gemm(const void* a, int32_t dtype, int64_t batch, int64_t rows, int64_t k,
+                        int64_t lda, int64_t a_batch_stride, const void* w, int64_t n,
+                        int32_t taps, int32_t tap_off0, int32_t tap_stride, int32_t splits, int32_t bn,
+                        int32_t mode, int32_t act, const void* bias, void* out, int64_t ldo,
+                        int64_t out_batch_stride, int64_t split_stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOLEY_B200_H_ */
