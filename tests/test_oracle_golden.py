@@ -1,0 +1,96 @@
+"""Pins the CPU oracle (oracle/foley_oracle.py) against outputs of the reference's own modules
+(tests/golden/*.pt, produced by tools/make_golden.py from /root/reference)."""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import foley_oracle as O
+from oracle import weights as W
+
+
+def _dit_inputs(c, B, L, Lv, S, seed=2):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, c["audio_vae_latent_dim"], L, generator=g)
+    t = torch.tensor([875.0, 120.0, 500.0, 999.0][:B])
+    cond = torch.randn(B, 77, c["condition_dim"], generator=g)
+    cond[:, 9:] = 0
+    clip = torch.randn(B, Lv, c["clip_dim"], generator=g)
+    sync = torch.randn(B, S, c["sync_feat_dim"], generator=g)
+    return x, t, cond, clip, sync
+
+
+@pytest.mark.parametrize("tag,policy,tol", [
+    ("tiny_fp32", "fp32", 1e-5),
+    ("small_fp32", "fp32", 1e-5),
+    # reference under the emulated CUDA-autocast cast policy (bf16): the oracle places the same rounding
+    # points; residual differences are fp32 summation order flipping a few bf16 roundings.
+    ("tiny_cudabf16", "cuda_bf16", 4e-3),
+    ("small_cudabf16", "cuda_bf16", 4e-3),
+])
+def test_dit_forward_matches_reference(golden_dir, tag, policy, tol):
+    gold = torch.load(os.path.join(golden_dir, f"dit_{tag}.pt"))
+    c = W.model_config(gold["config"])
+    sd = W.synth_dit_state_dict(c, seed=0)
+    sh = gold["shape"]
+    x, t, cond, clip, sync = _dit_inputs(c, sh["B"], sh["L"], sh["Lv"], sh["S"])
+    out = O.dit_forward(sd, c, x, t, cond, clip, sync, policy=policy)
+    assert out.shape == gold["out"].shape
+    assert rel_l2(out, gold["out"]) <= tol
+
+
+def test_bf16_policy_is_closer_to_bf16_reference_than_fp32_is(golden_dir):
+    """The cuda_bf16 policy must explain most of the bf16-vs-fp32 gap of the reference itself."""
+    g32 = torch.load(os.path.join(golden_dir, "dit_small_fp32.pt"))["out"]
+    g16 = torch.load(os.path.join(golden_dir, "dit_small_cudabf16.pt"))
+    c = W.model_config("small")
+    sd = W.synth_dit_state_dict(c, seed=0)
+    sh = g16["shape"]
+    out = O.dit_forward(sd, c, *_dit_inputs(c, sh["B"], sh["L"], sh["Lv"], sh["S"]), policy="cuda_bf16")
+    gap_ref = rel_l2(g16["out"], g32)
+    assert rel_l2(out, g16["out"]) < 0.5 * gap_ref
+
+
+@pytest.mark.parametrize("tag", ["tiny_t2a_nocfg", "tiny_v2a_cfg"])
+def test_denoise_loop_and_decode_match_reference(golden_dir, tag):
+    gold = torch.load(os.path.join(golden_dir, f"denoise_{tag}.pt"))
+    a = gold["args"]
+    c = W.model_config("tiny")
+    sd = W.synth_dit_state_dict(c, seed=0)
+    L, Lv, S = W.clip_lengths(a["duration"])
+    feats = W.synth_conditions(c, L, Lv, S)
+    if not a["v2a"]:
+        feats["siglip2_feat"] = sd["empty_clip_feat"][None].expand(1, Lv, -1)
+        feats["syncformer_feat"] = sd["empty_sync_feat"][None].expand(1, S, -1)
+    gen = torch.Generator(device="cpu").manual_seed(123)
+    noise = torch.randn((a["batch"], 128, L), generator=gen, dtype=torch.float32)
+    lat = O.denoise(sd, c, feats, noise, a["steps"], a["guidance"], policy="fp32")
+    assert rel_l2(lat, gold["latents"]) <= 2e-5
+    dsd = W.synth_dac_state_dict(W.DAC_TINY, seed=3)
+    wav = O.dac_decode(dsd, lat)
+    assert wav.shape == gold["audio"].shape
+    assert rel_l2(wav, gold["audio"].float()) <= 2e-3   # fixture stored as fp16
+
+
+def test_dac_decode_full_size_matches_reference(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "dac_full_L25.pt"))
+    dsd = W.synth_dac_state_dict(W.DAC_CONFIG, seed=3)
+    z = torch.randn(1, 128, 25, generator=torch.Generator().manual_seed(5))
+    wav = O.dac_decode(dsd, z)
+    assert wav.shape == (1, 1, 25 * 960)
+    assert rel_l2(wav, gold["wav"]) <= 1e-5
+
+
+def test_interleaved_rope_positions_closed_form():
+    """Closed form vs the reference's interpolate round trip (hifi_foley.py:35-60) on index tensors."""
+    import torch.nn.functional as F
+    for L, Lv in [(50, 8), (250, 40), (125, 20), (1500, 240), (3000, 480), (55, 8)]:
+        up = F.interpolate(torch.arange(Lv, dtype=torch.float32)[None, None], size=L, mode="nearest-exact")[0, 0]
+        slots = 2 * torch.arange(L, dtype=torch.float32) + 1           # odd slots carry the visual copies
+        back_pos = F.interpolate(slots[None, None], size=Lv, mode="nearest-exact")[0, 0].long()
+        back_tok = F.interpolate(up[None, None], size=Lv, mode="nearest-exact")[0, 0].long()
+        a_pos, v_pos = O.interleaved_positions(L, Lv)
+        assert torch.equal(v_pos, back_pos)
+        assert torch.equal(back_tok, torch.arange(Lv))
+        assert torch.equal(a_pos, 2 * torch.arange(L))

@@ -86,15 +86,15 @@ def install():
     dcfg.ConfigMixin, dcfg.register_to_config = ConfigMixin, register_to_config
     dutils = _mod("diffusers.utils")
 
-    class BaseOutput(dict):
-        def __init__(self, **kw):
-            super().__init__(**kw)
-            self.__dict__.update(kw)
+    class BaseOutput:
+        """diffusers.utils.BaseOutput stand-in: dataclass subclasses index like tuples (utils.py:246)."""
+
+        def to_tuple(self):
+            import dataclasses
+            return tuple(getattr(self, f.name) for f in dataclasses.fields(self))
 
         def __getitem__(self, k):
-            if isinstance(k, int):
-                return list(self.values())[k]
-            return super().__getitem__(k)
+            return self.to_tuple()[k] if isinstance(k, int) else getattr(self, k)
 
     dutils.BaseOutput = BaseOutput
 
