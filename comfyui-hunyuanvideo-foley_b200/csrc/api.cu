@@ -1,0 +1,155 @@
+// C-ABI entry points of libfoley_b200.so (include/foley_b200.h): thin, exception-free wrappers over Engine.
+#include <new>
+
+#include "common.cuh"
+#include "engine.cuh"
+#include "gemm_host.cuh"
+
+namespace foley {
+std::string& last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+}  // namespace foley
+
+using namespace foley;
+
+extern "C" const char* foley_last_error(void) { return last_error_ref().c_str(); }
+extern "C" const char* foley_version(void) { return "foley_b200 0.1 sm_100a (tcgen05+TMA)"; }
+
+extern "C" foley_status foley_gemm(const void* a, int32_t dtype, int64_t batch, int64_t rows, int64_t k,
+                                   int64_t lda, int64_t a_batch_stride, const void* w, int64_t n,
+                                   int32_t taps, int32_t tap_off0, int32_t tap_stride, int32_t splits,
+                                   int32_t bn, int32_t mode, int32_t act, const void* bias, void* out,
+                                   int64_t ldo, int64_t out_batch_stride, int64_t split_stride,
+                                   void* stream) {
+    if (!a || !w || !out) return fail(FOLEY_ERR_INVALID, "foley_gemm: null pointer");
+    if (dtype != FOLEY_DT_BF16 && dtype != FOLEY_DT_F32) return fail(FOLEY_ERR_INVALID, "foley_gemm: dtype");
+    if (mode < 0 || mode > 2) return fail(FOLEY_ERR_INVALID, "foley_gemm: mode must be 0,1,2");
+    GemmLaunch L;
+    L.a.ptr = a;
+    L.a.dtype = dtype == FOLEY_DT_BF16 ? DT_BF16 : DT_F32;
+    L.a.k = k; L.a.rows = rows; L.a.batch = batch; L.a.ld = lda; L.a.batch_stride = a_batch_stride;
+    L.w = w; L.n = n;
+    L.taps = taps; L.tap_off0 = tap_off0; L.tap_stride = tap_stride;
+    L.splits = splits; L.bn = bn & 0xFFFF;
+    L.dbg_stop = (bn >> 16) & 0xF;  // bring-up aid: upper bits of bn select a partial pipeline
+    L.epi.mode = mode; L.epi.act = act; L.epi.bias = bias; L.epi.out = out; L.epi.ldo = ldo;
+    L.epi.out_batch_stride = out_batch_stride; L.epi.split_stride = split_stride;
+    std::string err;
+    if (!launch_gemm(L, static_cast<cudaStream_t>(stream), &err)) return fail(FOLEY_ERR_CUDA, err);
+    return FOLEY_OK;
+}
+
+// Reads and clears the device debug words ([0] = first timed-out mbarrier wait code).
+extern "C" foley_status foley_debug_flags(uint32_t* out4) {
+    unsigned int h[4] = {0, 0, 0, 0};
+    FOLEY_CUDA_OK(cudaMemcpyFromSymbol(h, g_foley_dbg, sizeof h));
+    unsigned int z[4] = {0, 0, 0, 0};
+    FOLEY_CUDA_OK(cudaMemcpyToSymbol(g_foley_dbg, z, sizeof z));
+    for (int i = 0; i < 4; ++i) out4[i] = h[i];
+    return FOLEY_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ engine
+struct foley_engine {
+    Engine impl;
+};
+
+#define API_GUARD_BEGIN try {
+#define API_GUARD_END                                                          \
+    } catch (const std::bad_alloc&) {                                          \
+        return fail(FOLEY_ERR_CUDA, "out of host memory");                     \
+    } catch (const std::exception& ex) {                                       \
+        return fail(FOLEY_ERR_CUDA, std::string("internal error: ") + ex.what()); \
+    }
+
+extern "C" foley_status foley_engine_create(const foley_config* cfg, int device, foley_engine** out) {
+    if (!cfg || !out) return fail(FOLEY_ERR_INVALID, "foley_engine_create: null argument");
+    API_GUARD_BEGIN
+    foley_engine* e = new foley_engine();
+    foley_status s = e->impl.create(cfg, device);
+    if (s != FOLEY_OK) { delete e; return s; }
+    *out = e;
+    return FOLEY_OK;
+    API_GUARD_END
+}
+
+extern "C" void foley_engine_destroy(foley_engine* e) { delete e; }
+
+extern "C" foley_status foley_engine_load_tensor(foley_engine* e, const char* name, const void* data,
+                                                 const int64_t* shape, int32_t ndim, int32_t dtype) {
+    if (!e) return fail(FOLEY_ERR_INVALID, "null engine");
+    API_GUARD_BEGIN
+    return e->impl.load_tensor(name, data, shape, ndim, dtype);
+    API_GUARD_END
+}
+
+extern "C" foley_status foley_engine_finalize(foley_engine* e) {
+    if (!e) return fail(FOLEY_ERR_INVALID, "null engine");
+    API_GUARD_BEGIN
+    return e->impl.finalize();
+    API_GUARD_END
+}
+
+extern "C" foley_status foley_set_conditions(foley_engine* e, const void* clip, const void* sync, const void* text,
+                                             int32_t dtype, int32_t n_cond, int32_t Lv, int32_t S, int32_t T,
+                                             int32_t L, int32_t batch, void* stream) {
+    if (!e || !clip || !sync || !text) return fail(FOLEY_ERR_INVALID, "foley_set_conditions: null argument");
+    if (dtype != FOLEY_DT_BF16 && dtype != FOLEY_DT_F32 && dtype != FOLEY_DT_F16)
+        return fail(FOLEY_ERR_INVALID, "foley_set_conditions: dtype");
+    API_GUARD_BEGIN
+    return e->impl.set_conditions(clip, sync, text, dtype, n_cond, Lv, S, T, L, batch, e->impl.pick_stream(stream));
+    API_GUARD_END
+}
+
+extern "C" foley_status foley_dit_forward(foley_engine* e, const float* x, const float* t, int32_t n_t, float* out,
+                                          void* stream) {
+    if (!e || !x || !t || !out) return fail(FOLEY_ERR_INVALID, "foley_dit_forward: null argument");
+    API_GUARD_BEGIN
+    return e->impl.forward(x, t, n_t, out, e->impl.pick_stream(stream));
+    API_GUARD_END
+}
+
+extern "C" foley_status foley_denoise(foley_engine* e, float* latents, const float* sigmas, int32_t n_steps,
+                                      float guidance, foley_progress_fn progress, void* user, void* stream) {
+    if (!e || !latents || !sigmas) return fail(FOLEY_ERR_INVALID, "foley_denoise: null argument");
+    API_GUARD_BEGIN
+    return e->impl.denoise(latents, sigmas, n_steps, guidance, progress, user, e->impl.pick_stream(stream));
+    API_GUARD_END
+}
+
+extern "C" foley_status foley_dac_decode(foley_engine* e, const float* z, int32_t batch, int32_t L, float* wav,
+                                         void* stream) {
+    if (!e || !z || !wav) return fail(FOLEY_ERR_INVALID, "foley_dac_decode: null argument");
+    API_GUARD_BEGIN
+    if (!e->impl.dac_ready) {
+        foley_status s = e->impl.dac_finalize();
+        if (s != FOLEY_OK) return s;
+    }
+    return e->impl.dac_decode(z, batch, L, wav, e->impl.pick_stream(stream));
+    API_GUARD_END
+}
+
+extern "C" int64_t foley_launch_count(const foley_engine* e) { return e ? e->impl.launches : 0; }
+
+extern "C" foley_status foley_debug_read(foley_engine* e, const char* what, float* dst, int64_t cap, int64_t* n_out) {
+    if (!e) return fail(FOLEY_ERR_INVALID, "null engine");
+    API_GUARD_BEGIN
+    return e->impl.debug_read(what, dst, cap, n_out);
+    API_GUARD_END
+}
+
+// Runtime switches for tests / profiling: "cuda_graph" (0/1), "max_splits" (1..8).
+extern "C" foley_status foley_engine_set_option(foley_engine* e, const char* key, int64_t value) {
+    if (!e || !key) return fail(FOLEY_ERR_INVALID, "null argument");
+    const std::string k(key);
+    if (k == "cuda_graph") { e->impl.use_cuda_graph = value != 0; e->impl.graph_valid = false; }
+    else if (k == "max_splits") {
+        if (value < 1 || value > 8) return fail(FOLEY_ERR_INVALID, "max_splits must be in [1,8]");
+        if (e->impl.plan.valid && value > e->impl.max_splits) return fail(FOLEY_ERR_STATE, "raise max_splits before set_conditions");
+        e->impl.max_splits_used = static_cast<int>(value);
+        e->impl.graph_valid = false;
+    } else return fail(FOLEY_ERR_INVALID, "unknown option " + k);
+    return FOLEY_OK;
+}

@@ -1,0 +1,141 @@
+// Engine state: weights in GEMM-ready device layout, activation buffers sized per "plan"
+// (batch, lengths), and the launch sequence of one DiT step.  See DESIGN.md for the data layout.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_host.cuh"
+#include "rowwise.cuh"
+
+namespace foley {
+
+using bf16 = __nv_bfloat16;
+
+struct RawTensor {
+    void* dev = nullptr;          // device copy in source dtype
+    std::vector<int64_t> shape;
+    int dtype = FOLEY_DT_BF16;
+    int64_t numel = 0;
+};
+
+struct LinearW {                  // K-major weight [N, Ktot] + optional bias [N]
+    bf16* w = nullptr;
+    bf16* b = nullptr;
+    int n = 0, k = 0, taps = 1;   // k = per-tap K
+};
+
+struct TripleW {
+    LinearW qkv[2], self_proj[2], cross_q[2], cross_proj[2], fc1[2], fc2[2];   // [0]=audio, [1]=v_cond
+    bf16* self_q_norm[2] = {nullptr, nullptr};
+    bf16* self_k_norm[2] = {nullptr, nullptr};
+    bf16* cross_q_norm[2] = {nullptr, nullptr};
+    bf16* text_k_norm = nullptr;
+};
+struct SingleW {
+    LinearW qkv, linear1, w13, w2;
+    bf16* q_norm = nullptr;
+    bf16* k_norm = nullptr;
+};
+
+struct DacLayer;  // dac.cuh
+
+struct Plan {                     // shapes of the current generation
+    int B = 0, U = 0, B2 = 0, G = 0, L = 0, Lv = 0, S = 0, T = 0, n_t = 0;
+    bool valid = false;
+};
+
+class Engine {
+  public:
+    foley_config cfg{};
+    int device = 0;
+    int C = 0, H = 0, NT = 0, NS = 0, F = 0, Hs = 0, Hy = 0, LAT = 0;
+    int64_t launches = 0;
+    bool finalized = false;
+    std::unordered_map<std::string, RawTensor> raw;
+
+    // ---- DiT weights
+    LinearW audio_embed, vis_w13, vis_w2, cond1, cond2, time1, time2, sync0, sync_w13, sync_w2, final_lin;
+    LinearW mod_triple_all;       // [NT*2*9C, C]: block i audio rows [i*18C, +9C), v_cond rows [i*18C+9C, +9C)
+    LinearW mod_single_all;       // [NS*6C, C]
+    LinearW text_kv_all;          // [NT*2C, C]
+    bf16* sync_pos_emb = nullptr; // [8, sync_dim]
+    bf16* empty_clip = nullptr;   // [clip_dim]
+    bf16* empty_sync = nullptr;   // [sync_dim]
+    std::vector<TripleW> triple;
+    std::vector<SingleW> single;
+
+    // ---- plan + buffers
+    Plan plan;
+    std::vector<void*> plan_allocs;
+    // conditions / per-generation
+    bf16 *a_sync = nullptr, *vcond0 = nullptr, *text_k = nullptr, *text_v = nullptr;
+    float *rope_av_a_cos = nullptr, *rope_av_a_sin = nullptr, *rope_av_v_cos = nullptr, *rope_av_v_sin = nullptr;
+    float *rope_plain_cos = nullptr, *rope_plain_sin = nullptr;
+    int *grp_of_sample = nullptr, *trow_of_grp = nullptr, *cond_of_grp = nullptr, *step_dev = nullptr;
+    float *sigmas_dev = nullptr, *t_dev = nullptr;
+    bf16 *vec_all = nullptr, *mod_triple = nullptr;
+    // per-step activations
+    bf16 *x_in = nullptr, *h_a = nullptr, *h_v = nullptr, *qkv_a = nullptr, *qkv_v = nullptr;
+    bf16 *Qj = nullptr, *Kj = nullptr, *Vj = nullptr, *attn_out = nullptr, *mlp_a = nullptr, *mlp_v = nullptr;
+    bf16 *vectok_act = nullptr, *mod_single = nullptr, *y_out = nullptr;
+    float *audio = nullptr, *vcond = nullptr, *part_a = nullptr, *part_v = nullptr, *lat_dev = nullptr;
+    int max_splits = 8;          // workspace capacity
+    int max_splits_used = 8;     // runtime cap (<= max_splits)
+    cudaGraphExec_t step_graph = nullptr;
+    bool graph_valid = false;
+    bool use_cuda_graph = true;
+    float graph_guidance = 0.f;
+    int64_t graph_launches_per_step = 0;
+    int cur_G = 1;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr;   // blocking stream used when the caller passes NULL (legacy stream cannot be captured)
+    // scratch of set_conditions / prepare_timesteps (plan-owned)
+    bf16 *sc_clip = nullptr, *sc_sync = nullptr, *sc_text = nullptr, *sc_s0 = nullptr, *sc_s1 = nullptr, *sc_s2 = nullptr;
+    bf16 *sc_s3 = nullptr, *sc_c1 = nullptr, *sc_c2 = nullptr, *sc_kv = nullptr, *sc_v1 = nullptr;
+    bf16 *sc_e = nullptr, *sc_h1 = nullptr, *sc_vs = nullptr;
+    int* sc_idx = nullptr;
+    cudaStream_t pick_stream(void* st) { return st ? static_cast<cudaStream_t>(st) : own_stream; }
+
+    // ---- DAC
+    std::vector<DacLayer*> dac_layers;
+    bool dac_ready = false;
+    std::vector<void*> dac_allocs;
+    int64_t dac_cap_T = 0;
+    float *dac_buf[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t dac_buf_elems = 0;
+
+    ~Engine();
+    foley_status create(const foley_config* c, int dev);
+    foley_status load_tensor(const char* name, const void* data, const int64_t* shape, int ndim, int dtype);
+    foley_status finalize();
+    foley_status set_conditions(const void* clip, const void* sync, const void* text, int dtype, int U, int Lv,
+                                int S, int T, int L, int B, cudaStream_t st);
+    foley_status prepare_timesteps(const float* t_host, int n_t, bool per_sample, cudaStream_t st);
+    foley_status step(cudaStream_t st);                 // one forward: x_in -> y_out
+    foley_status forward(const float* x, const float* t, int n_t, float* out, cudaStream_t st);
+    foley_status denoise(float* latents, const float* sigmas, int n_steps, float guidance,
+                         foley_progress_fn progress, void* user, cudaStream_t st);
+    foley_status dac_finalize();
+    foley_status dac_decode(const float* z, int batch, int L, float* wav, cudaStream_t st);
+    foley_status debug_read(const char* what, float* dst, int64_t cap, int64_t* n_out);
+
+  private:
+    foley_status take_linear(const std::string& name, LinearW* out, bool bias, int taps_expected);
+    foley_status take_vec(const std::string& name, bf16** out, int64_t n_expected);
+    foley_status raw_as_bf16(const std::string& name, bf16** out, RawTensor** rt);
+    foley_status gemm(cudaStream_t st, const bf16* A, int rows, int batch, long long lda, long long a_bs,
+                      const LinearW& W, int n_off, int n_cnt, GemmEpi epi, int splits, int bn);
+    foley_status alloc_plan(int B, int U, int L, int Lv, int S, int T);
+    void free_plan();
+    template <typename T> foley_status palloc(T** p, size_t count);
+    int pick_splits(int rows, int batch, int n, int kblocks, int bn) const;
+    foley_status proj_combine(cudaStream_t st, const bf16* A, int rows, int batch, long long lda, long long a_bs,
+                              const LinearW& W, float* partials, CombineArgs ca);
+};
+
+}  // namespace foley

@@ -94,10 +94,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
+    const int n0 = blockIdx.y * BN;
     const int m_tiles = (g.rows + Cfg::BM - 1) / Cfg::BM;
-    const int batch = blockIdx.y / m_tiles;
-    const int m0 = (blockIdx.y % m_tiles) * Cfg::BM;
+    const int batch = blockIdx.x / m_tiles;          // x carries (batch, m-tile): it may exceed 65535 (DAC)
+    const int m0 = (blockIdx.x % m_tiles) * Cfg::BM;
     const int split = blockIdx.z;
 
     const int kb_total = g.taps * g.kb_per_tap;

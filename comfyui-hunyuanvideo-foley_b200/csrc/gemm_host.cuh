@@ -81,6 +81,7 @@ struct GemmLaunch {
     int splits = 1;
     int bn = 128;              // tile width: 64, 128 or 256
     int dbg_stop = 0;
+    long long out_rows = 0;    // output rows per sample (0 -> a.rows); may exceed a.rows (halo rows read as zero)
     GemmEpi epi;
 };
 
@@ -91,12 +92,36 @@ inline cudaError_t launch_gemm_inst(const CUtensorMap& ma, const CUtensorMap& mb
     auto kern = gemm_tcgen05_kernel<BN, kTF32>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cs);
+        if (cs == cudaStreamCaptureStatusNone) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
     }
     kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, args);
     return cudaGetLastError();
+}
+
+// Opts every instantiation into its dynamic shared-memory size up front (must not happen lazily inside a
+// stream capture).
+inline bool gemm_init_attributes(std::string* err) {
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto kern, int bytes) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    set(gemm_tcgen05_kernel<64, false>, GemmCfg<64, false>::SMEM_BYTES);
+    set(gemm_tcgen05_kernel<128, false>, GemmCfg<128, false>::SMEM_BYTES);
+    set(gemm_tcgen05_kernel<256, false>, GemmCfg<256, false>::SMEM_BYTES);
+    set(gemm_tcgen05_kernel<64, true>, GemmCfg<64, true>::SMEM_BYTES);
+    set(gemm_tcgen05_kernel<128, true>, GemmCfg<128, true>::SMEM_BYTES);
+    set(gemm_tcgen05_kernel<256, true>, GemmCfg<256, true>::SMEM_BYTES);
+    if (e != cudaSuccess) {
+        if (err) *err = std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e);
+        return false;
+    }
+    return true;
 }
 
 inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* err) {
@@ -112,7 +137,8 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
     if (!encode_operand_map(&mb, wb, L.bn, err)) return false;
 
     GemmArgs args;
-    args.rows = static_cast<int>(L.a.rows);
+    const long long out_rows = L.out_rows > 0 ? L.out_rows : L.a.rows;
+    args.rows = static_cast<int>(out_rows);
     args.n = static_cast<int>(L.n);
     args.kb_per_tap = static_cast<int>(L.a.k / bk);
     args.taps = L.taps;
@@ -121,9 +147,9 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
     args.splits = L.splits < 1 ? 1 : L.splits;
     args.epi = L.epi;
     args.dbg_stop = L.dbg_stop;
-    const int m_tiles = static_cast<int>((L.a.rows + 127) / 128);
-    dim3 grid(static_cast<unsigned>((L.n + L.bn - 1) / L.bn),
-              static_cast<unsigned>(m_tiles * (L.a.batch > 0 ? L.a.batch : 1)), static_cast<unsigned>(args.splits));
+    const int m_tiles = static_cast<int>((out_rows + 127) / 128);
+    dim3 grid(static_cast<unsigned>(m_tiles * (L.a.batch > 0 ? L.a.batch : 1)),
+              static_cast<unsigned>((L.n + L.bn - 1) / L.bn), static_cast<unsigned>(args.splits));
     cudaError_t e = cudaSuccess;
     if (!tf32) {
         if (L.bn == 64) e = launch_gemm_inst<64, false>(ma, mb, args, grid, stream);

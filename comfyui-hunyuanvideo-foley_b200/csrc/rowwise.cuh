@@ -1,0 +1,464 @@
+// Row-wise (HBM/L2-bound) kernels of the DiT step: everything between the tensor-core GEMMs.
+// One warp owns one token row (C <= 2048 channels kept in registers), so LayerNorm statistics are
+// warp-shuffle reductions and every global access is a coalesced 8/16-byte vector.
+//
+// Rounding points follow the reference's CUDA-autocast dataflow (oracle/foley_oracle.py "cuda_bf16",
+// SURVEY.md Appendix B): fp32 LayerNorm, (1+scale) rounded to bf16, result rounded to bf16 for the next
+// GEMM; bf16 gate multiply; fp32 audio residual stream, bf16-valued visual stream.
+#pragma once
+#include "ptx.cuh"
+
+namespace foley {
+
+constexpr int kMaxVecPerLane = 16;  // C <= 32 lanes * 16 * 4 = 2048
+
+// Where a row finds its modulation vectors (shift / scale / gate), all bf16:
+//   ptr = base + grp_or_trow * sample_stride + l * tok_stride + chunk * C
+// by_trow = 1: triple blocks, indexed by the timestep row of the sample's group (per-sample vectors);
+// by_trow = 0: single blocks, indexed by the sample's group, per-token vectors.
+struct ModRef {
+    const __nv_bfloat16* base = nullptr;
+    long long sample_stride = 0;
+    long long tok_stride = 0;
+    int by_trow = 0;
+};
+
+struct RowMap {
+    const int* grp_of_sample;  // [B2]
+    const int* trow_of_grp;    // [G]
+    const int* cond_of_grp;    // [G]
+    int L;                     // rows (tokens) per sample
+};
+
+__device__ __forceinline__ const __nv_bfloat16* mod_ptr(const ModRef& m, const RowMap& rm, int b, int l, int chunk, int C) {
+    const int g = rm.grp_of_sample[b];
+    const long long s = m.by_trow ? rm.trow_of_grp[g] : g;
+    return m.base + s * m.sample_stride + static_cast<long long>(l) * m.tok_stride + static_cast<long long>(chunk) * C;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void load_bf16x4(const __nv_bfloat16* p, float (&o)[4]) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
+}
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, const float (&v)[4]) {
+    uint2 u;
+    u.x = pack_bf16x2(v[0], v[1]);
+    u.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+// LayerNorm (no affine) of a register-resident row, two-pass in fp32 like ATen's CUDA kernel.
+template <int NV>
+__device__ __forceinline__ void row_layer_norm(float (&x)[NV][4], int nvec, int C, float eps) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (i < nvec) s += (x[i][0] + x[i][1]) + (x[i][2] + x[i][3]);
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (i < nvec) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float d = x[i][j] - mean; q += d * d; }
+        }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (i < nvec) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[i][j] = (x[i][j] - mean) * rstd;
+        }
+}
+
+struct CombineArgs {
+    // ---- residual update (skipped when partials == nullptr):
+    //   y = bf16r(sum_s partials[s][row] + bias);  if gate: y = bf16r(y * gate);  x = x_src + y
+    const float* partials = nullptr;     // [splits][rows_total][C]
+    int splits = 0;
+    long long split_stride = 0;
+    const __nv_bfloat16* bias = nullptr; // [C] or null
+    ModRef gate;                         // gate.base == nullptr -> no gate
+    int gate_chunk = 0;
+    float* x = nullptr;                  // residual stream fp32 [B2*L][C] (in/out)
+    const __nv_bfloat16* x_init = nullptr;  // if set: x_src = x_init[cond_of_grp, l] (bf16, first layer) instead of x
+    int round_x = 0;                     // 1: keep the stream bf16-valued (visual stream)
+    // ---- LayerNorm + modulate (skipped when h == nullptr):
+    //   h = bf16r(LN(x) * bf16r(1 + scale) + shift)
+    __nv_bfloat16* h = nullptr;          // [B2*L][C]
+    float eps = 1e-6f;
+    ModRef mod;                          // mod.base == nullptr -> plain LN
+    int shift_chunk = 0, scale_chunk = 1;
+    int C = 0;
+    int rows_total = 0;
+    RowMap rm;
+};
+
+// grid: ceil(rows_total / 4) blocks of 128 threads; one warp per row.
+__global__ void __launch_bounds__(128) combine_ln_mod_kernel(const CombineArgs a) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= a.rows_total) return;
+    const int b = row / a.rm.L, l = row - b * a.rm.L;
+    const int C = a.C;
+    const int nvec = C / 128;  // float4 vectors per lane (C is a multiple of 128)
+    float x[kMaxVecPerLane][4];
+    float* xrow = a.x + static_cast<long long>(row) * C;
+
+    if (a.x_init) {
+        const int g = a.rm.grp_of_sample[b];
+        const __nv_bfloat16* src = a.x_init + (static_cast<long long>(a.rm.cond_of_grp[g]) * a.rm.L + l) * C;
+#pragma unroll
+        for (int i = 0; i < kMaxVecPerLane; ++i)
+            if (i < nvec) load_bf16x4(src + (i * 32 + lane) * 4, x[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kMaxVecPerLane; ++i)
+            if (i < nvec) {
+                const float4 v = *reinterpret_cast<const float4*>(xrow + (i * 32 + lane) * 4);
+                x[i][0] = v.x; x[i][1] = v.y; x[i][2] = v.z; x[i][3] = v.w;
+            }
+    }
+
+    if (a.partials) {
+        const __nv_bfloat16* gate = a.gate.base ? mod_ptr(a.gate, a.rm, b, l, a.gate_chunk, C) : nullptr;
+#pragma unroll
+        for (int i = 0; i < kMaxVecPerLane; ++i)
+            if (i < nvec) {
+                const int c = (i * 32 + lane) * 4;
+                float4 acc = *reinterpret_cast<const float4*>(a.partials + static_cast<long long>(row) * C + c);
+                for (int s = 1; s < a.splits; ++s) {
+                    const float4 p = *reinterpret_cast<const float4*>(a.partials + s * a.split_stride +
+                                                                      static_cast<long long>(row) * C + c);
+                    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+                }
+                float y[4] = {acc.x, acc.y, acc.z, acc.w};
+                if (a.bias) {
+                    float bv[4];
+                    load_bf16x4(a.bias + c, bv);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) y[j] += bv[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) y[j] = bf16_round(y[j]);
+                if (gate) {
+                    float gv[4];
+                    load_bf16x4(gate + c, gv);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) y[j] = bf16_round(y[j] * gv[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    x[i][j] += y[j];
+                    if (a.round_x) x[i][j] = bf16_round(x[i][j]);
+                }
+            }
+    }
+    if (a.partials || a.x_init) {
+#pragma unroll
+        for (int i = 0; i < kMaxVecPerLane; ++i)
+            if (i < nvec)
+                *reinterpret_cast<float4*>(xrow + (i * 32 + lane) * 4) = make_float4(x[i][0], x[i][1], x[i][2], x[i][3]);
+    }
+
+    if (a.h) {
+        row_layer_norm<kMaxVecPerLane>(x, nvec, C, a.eps);
+        const __nv_bfloat16* sh = a.mod.base ? mod_ptr(a.mod, a.rm, b, l, a.shift_chunk, C) : nullptr;
+        const __nv_bfloat16* sc = a.mod.base ? mod_ptr(a.mod, a.rm, b, l, a.scale_chunk, C) : nullptr;
+        __nv_bfloat16* hrow = a.h + static_cast<long long>(row) * C;
+#pragma unroll
+        for (int i = 0; i < kMaxVecPerLane; ++i)
+            if (i < nvec) {
+                const int c = (i * 32 + lane) * 4;
+                float o[4] = {x[i][0], x[i][1], x[i][2], x[i][3]};
+                if (sh) {
+                    float sv[4], cv[4];
+                    load_bf16x4(sh + c, sv);
+                    load_bf16x4(sc + c, cv);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = __fadd_rn(__fmul_rn(o[j], bf16_round(1.0f + cv[j])), sv[j]);
+                }
+                store_bf16x4(hrow + c, o);
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// q/k RMSNorm + RoPE + scatter into the attention layout [B, H, S_total, D] (D = 128; one warp per
+// (row, head), 4 consecutive channels per lane so each rotation pair lives in one thread).
+//   norm_kind 0: reference RMSNorm (norm_layers.py:49-51): bf16r(bf16r(x * rstd(eps=1e-6)) * w)
+//   norm_kind 1: torch.nn.RMSNorm(eps=None) on bf16: bf16r(x * rstd(eps=fp32 eps) * w)
+struct QkvPart {
+    __nv_bfloat16* dst = nullptr;        // [B][H][S_total][128]
+    long long dst_batch_stride = 0;      // elements
+    long long dst_head_stride = 0;
+    int seq_offset = 0;                  // row l lands at seq_offset + l
+    const __nv_bfloat16* norm_w = nullptr;  // [128]; nullptr -> plain copy (v)
+    int src_col = 0;                     // column offset of this part inside the source row
+};
+
+struct QkvArgs {
+    const __nv_bfloat16* src = nullptr;  // [B*L][src_ld], parts laid out (part, H, D)
+    int src_ld = 0;
+    int n_parts = 0;
+    QkvPart part[3];
+    int H = 0;
+    int L = 0;                           // rows per sample
+    int rows_total = 0;
+    int norm_kind = 0;
+    float eps = 1e-6f;
+    const float* cos = nullptr;          // [P][128] fp32 tables
+    const float* sin = nullptr;
+    const int* pos = nullptr;            // [L] table row of token l; nullptr -> l
+};
+
+__global__ void __launch_bounds__(128) qk_norm_rope_kernel(const QkvArgs a) {
+    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int per_row = a.n_parts * a.H;
+    if (w >= a.rows_total * per_row) return;
+    const int row = w / per_row;
+    const int ph = w - row * per_row;
+    const int part = ph / a.H, head = ph - part * a.H;
+    const int b = row / a.L, l = row - b * a.L;
+    const QkvPart& p = a.part[part];
+    float v[4];
+    load_bf16x4(a.src + static_cast<long long>(row) * a.src_ld + p.src_col + head * 128 + lane * 4, v);
+    if (p.norm_w) {
+        const float ss = warp_sum(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+        const float rstd = rsqrtf(ss * (1.0f / 128.0f) + a.eps);
+        float wv[4];
+        load_bf16x4(p.norm_w + lane * 4, wv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (a.norm_kind == 0) v[j] = bf16_round(bf16_round(v[j] * rstd) * wv[j]);
+            else v[j] = bf16_round(__fmul_rn(__fmul_rn(v[j], rstd), wv[j]));
+        }
+        const int prow = a.pos ? a.pos[l] : l;
+        const float4 c = *reinterpret_cast<const float4*>(a.cos + static_cast<long long>(prow) * 128 + lane * 4);
+        const float4 s = *reinterpret_cast<const float4*>(a.sin + static_cast<long long>(prow) * 128 + lane * 4);
+        // (x0, x1) -> (x0*cos - x1*sin, x1*cos + x0*sin)   (attn_layers.py:112-148)
+        const float o0 = __fadd_rn(__fmul_rn(v[0], c.x), __fmul_rn(-v[1], s.x));
+        const float o1 = __fadd_rn(__fmul_rn(v[1], c.y), __fmul_rn(v[0], s.y));
+        const float o2 = __fadd_rn(__fmul_rn(v[2], c.z), __fmul_rn(-v[3], s.z));
+        const float o3 = __fadd_rn(__fmul_rn(v[3], c.w), __fmul_rn(v[2], s.w));
+        v[0] = o0; v[1] = o1; v[2] = o2; v[3] = o3;
+    }
+    __nv_bfloat16* dst = p.dst + static_cast<long long>(b) * p.dst_batch_stride +
+                         static_cast<long long>(head) * p.dst_head_stride +
+                         static_cast<long long>(p.seq_offset + l) * 128 + lane * 4;
+    store_bf16x4(dst, v);
+}
+
+// ------------------------------------------------------------------------------------------------ small ops
+// e[r, :] = bf16r([cos(t*f), sin(t*f)]), f_k = exp(-ln(1e4) * k / half)   (embed_layers.py:76-103)
+__global__ void timestep_embed_kernel(const float* t, int n_t, int dim, __nv_bfloat16* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = dim / 2;
+    if (i >= n_t * half) return;
+    const int r = i / half, k = i - r * half;
+    const float f = expf(-9.210340371976184f * static_cast<float>(k) / static_cast<float>(half));
+    const float arg = t[r] * f;
+    out[static_cast<long long>(r) * dim + k] = __float2bfloat16_rn(cosf(arg));
+    out[static_cast<long long>(r) * dim + half + k] = __float2bfloat16_rn(sinf(arg));
+}
+
+// out = bf16r(silu(in)) elementwise over bf16 (ModulateDiT's activation on the bf16 time vector).
+__global__ void silu_bf16_kernel(const __nv_bfloat16* in, __nv_bfloat16* out, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = __bfloat162float(in[i]);
+    out[i] = __float2bfloat16_rn(x / (1.0f + expf(-x)));
+}
+
+// out[g, l, :] = bf16r(silu(float(a_sync[cond(g), l, :]) + float(vec[trow(g), :])))   (hifi_foley.py:866-867
+// followed by ModulateDiT's SiLU on the fp32 per-token condition)
+__global__ void vectok_silu_kernel(const __nv_bfloat16* a_sync, const __nv_bfloat16* vec, const int* cond_of_grp,
+                                   const int* trow_of_grp, int G, int L, int C, __nv_bfloat16* out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long n4 = static_cast<long long>(G) * L * C / 4;
+    if (i >= n4) return;
+    const long long e = i * 4;
+    const int c = static_cast<int>(e % C);
+    const long long gl = e / C;
+    const int l = static_cast<int>(gl % L), g = static_cast<int>(gl / L);
+    float a[4], v[4], o[4];
+    load_bf16x4(a_sync + (static_cast<long long>(cond_of_grp[g]) * L + l) * C + c, a);
+    load_bf16x4(vec + static_cast<long long>(trow_of_grp[g]) * C + c, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float s = a[j] + v[j];
+        o[j] = s / (1.0f + expf(-s));
+    }
+    store_bf16x4(out + e, o);
+}
+
+// sync features: out[u, s, :] = bf16r(sync[u, s, :] + pos_emb[s % 8, :])   (hifi_foley.py:757-758)
+__global__ void sync_add_pos_kernel(const __nv_bfloat16* sync, const __nv_bfloat16* pos_emb, long long rows, int dim,
+                                    int S, __nv_bfloat16* out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= rows * dim) return;
+    const int c = static_cast<int>(i % dim);
+    const long long r = i / dim;
+    const int s = static_cast<int>(r % S);
+    out[i] = __float2bfloat16_rn(__bfloat162float(sync[i]) + __bfloat162float(pos_emb[(s & 7) * dim + c]));
+}
+
+// nearest-exact gather along the sequence: out[u, l, :] = in[u, idx[l], :]
+__global__ void gather_rows_kernel(const __nv_bfloat16* in, const int* idx, int U, int S, int L, int C,
+                                   __nv_bfloat16* out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long n8 = static_cast<long long>(U) * L * C / 8;
+    if (i >= n8) return;
+    const long long e = i * 8;
+    const int c = static_cast<int>(e % C);
+    const long long ul = e / C;
+    const int l = static_cast<int>(ul % L), u = static_cast<int>(ul / L);
+    *reinterpret_cast<uint4*>(out + e) =
+        *reinterpret_cast<const uint4*>(in + (static_cast<long long>(u) * S + idx[l]) * C + c);
+}
+
+// latents fp32 [B, ch, L] -> model input bf16 [B2, L, ch] for every group copy (utils.py:205,223)
+__global__ void latents_to_tokens_kernel(const float* lat, int B, int n_rep, int ch, int L, __nv_bfloat16* out) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, l = l0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < ch && l < L) ? lat[(static_cast<long long>(b) * ch + c) * L + l] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int l = l0 + i, c = c0 + threadIdx.x;
+        if (l < L && c < ch) {
+            const __nv_bfloat16 v = __float2bfloat16_rn(tile[threadIdx.x][i]);
+            for (int r = 0; r < n_rep; ++r)
+                out[((static_cast<long long>(r) * B + b) * L + l) * ch + c] = v;
+        }
+    }
+}
+
+// model output bf16 [B2, L, ch] -> fp32 [B2, ch, L]   (unpatchify1d, hifi_foley.py:926-936)
+__global__ void tokens_to_channels_kernel(const __nv_bfloat16* y, int B2, int ch, int L, float* out) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int l = l0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < ch && l < L) ? __bfloat162float(y[(static_cast<long long>(b) * L + l) * ch + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, l = l0 + threadIdx.x;
+        if (c < ch && l < L) out[(static_cast<long long>(b) * ch + c) * L + l] = tile[threadIdx.x][i];
+    }
+}
+
+// CFG combine (bf16, utils.py:241-243) + Euler update (fp32, scheduling_flow_match_discrete.py:262-297) +
+// next step's bf16 model input.  y: [n_cond*B, L, ch] bf16 (uncond rows first); latents [B, ch, L] fp32.
+// step_state: [0] = step index (incremented by thread 0 of block 0 after use), sigmas on device.
+__global__ void cfg_euler_kernel(const __nv_bfloat16* y, float* lat, __nv_bfloat16* x_next, int B, int n_cond,
+                                 int ch, int L, float guidance, const float* sigmas, const int* step_ptr) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+    const int step = *step_ptr;
+    const float dt = sigmas[step + 1] - sigmas[step];
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int l = l0 + i, c = c0 + threadIdx.x;
+        float v = 0.f;
+        if (l < L && c < ch) {
+            if (n_cond == 2) {
+                const float u = __bfloat162float(y[(static_cast<long long>(b) * L + l) * ch + c]);
+                const float t = __bfloat162float(y[(static_cast<long long>(B + b) * L + l) * ch + c]);
+                v = bf16_round(u + bf16_round(guidance * bf16_round(t - u)));
+            } else {
+                v = __bfloat162float(y[(static_cast<long long>(b) * L + l) * ch + c]);
+            }
+        }
+        tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, l = l0 + threadIdx.x;
+        if (c < ch && l < L) {
+            const long long o = (static_cast<long long>(b) * ch + c) * L + l;
+            const float nv = __fadd_rn(lat[o], __fmul_rn(tile[threadIdx.x][i], dt));
+            lat[o] = nv;
+            tile[threadIdx.x][i] = nv;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int l = l0 + i, c = c0 + threadIdx.x;
+        if (l < L && c < ch) {
+            const __nv_bfloat16 v = __float2bfloat16_rn(tile[i][threadIdx.x]);
+            for (int r = 0; r < n_cond; ++r)
+                x_next[((static_cast<long long>(r) * B + b) * L + l) * ch + c] = v;
+        }
+    }
+}
+
+// Advances the device-side step counter and the per-group timestep rows (one tiny launch per step so the
+// whole step can be replayed as one CUDA graph).
+__global__ void advance_step_kernel(int* step_ptr, int* trow_of_grp, int G) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int s = *step_ptr + 1;
+        *step_ptr = s;
+        for (int g = 0; g < G; ++g) trow_of_grp[g] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ weight repack
+__global__ void convert_to_bf16_kernel(const void* src, int src_dtype, long long n, __nv_bfloat16* dst) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v;
+    if (src_dtype == 0) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
+    else if (src_dtype == 1) v = reinterpret_cast<const float*>(src)[i];
+    else v = __half2float(reinterpret_cast<const __half*>(src)[i]);
+    dst[i] = __float2bfloat16_rn(v);
+}
+__global__ void convert_to_f32_kernel(const void* src, int src_dtype, long long n, float* dst) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v;
+    if (src_dtype == 0) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
+    else if (src_dtype == 1) v = reinterpret_cast<const float*>(src)[i];
+    else v = __half2float(reinterpret_cast<const __half*>(src)[i]);
+    dst[i] = v;
+}
+
+// Conv weight [N, K, taps] -> tap-major GEMM rows dst[(n*row_mul + row_add) , tap*K + k]; also used for plain
+// [N, K] matrices (taps = 1).  row_mul/row_add interleave two matrices (SwiGLU w1/w3 pairs).
+__global__ void repack_conv_weight_kernel(const __nv_bfloat16* src, int N, int K, int taps, int row_mul, int row_add,
+                                          __nv_bfloat16* dst) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(N) * K * taps;
+    if (i >= total) return;
+    const int k = static_cast<int>(i % K);
+    const int tap = static_cast<int>((i / K) % taps);
+    const int n = static_cast<int>(i / (static_cast<long long>(K) * taps));
+    dst[(static_cast<long long>(n) * row_mul + row_add) * (static_cast<long long>(K) * taps) + static_cast<long long>(tap) * K + k] =
+        src[(static_cast<long long>(n) * K + k) * taps + tap];
+}
+
+// Single-block QKV rows (H D K) -> (K H D)   (hifi_foley.py:362): dst row (k*H*D + h*D + d) = src row (h*D*3 + d*3 + k)
+__global__ void permute_qkv_rows_kernel(const __nv_bfloat16* src, int H, int D, long long row_len, __nv_bfloat16* dst) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(3) * H * D * row_len;
+    if (i >= total) return;
+    const long long col = i % row_len;
+    const long long drow = i / row_len;
+    const int k = static_cast<int>(drow / (H * D));
+    const int hd = static_cast<int>(drow % (H * D));
+    const int h = hd / D, d = hd % D;
+    dst[i] = src[(static_cast<long long>(h) * D * 3 + d * 3 + k) * row_len + col];
+}
+
+}  // namespace foley

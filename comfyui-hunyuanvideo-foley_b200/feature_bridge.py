@@ -1,0 +1,50 @@
+"""Bridge to the condition encoders (SigLIP2, Synchformer, CLAP) — OUT OF THIS ENGINE'S SCOPE (SURVEY.md §8f:
+they run once per clip, before the denoise path).  When the reference's model package `hunyuanvideo_foley`
+and the HF checkpoints are available, this borrows them and exposes the single callable the Sampler needs:
+
+    extract_features(frames_8fps|None, frames_25fps|None, prompt, negative_prompt)
+        -> (visual_feats, text_feats, audio_len_in_s)
+
+with the tensors the reference's `feature_process_from_tensors` returns (reference utils.py:262-292).
+"""
+import torch
+
+
+def load_reference_extractors(synchformer_path, device):
+    from torchvision.transforms import v2
+    from transformers import AutoModel, AutoTokenizer, ClapTextModelWithProjection
+    from hunyuanvideo_foley.models.synchformer import Synchformer          # reference package, if installed
+    from hunyuanvideo_foley.utils.feature_utils import (encode_text_feat, encode_video_with_siglip2,
+                                                        encode_video_with_sync)
+    from .config import AttributeDict
+
+    sd = torch.load(synchformer_path, map_location="cpu", weights_only=False)
+    sync_model = Synchformer()
+    sync_model.load_state_dict(sd, strict=False)
+    deps = AttributeDict({
+        "syncformer_model": sync_model.to(device).eval(),
+        "siglip2_model": AutoModel.from_pretrained("google/siglip2-base-patch16-512").to(device).eval(),
+        "clap_tokenizer": AutoTokenizer.from_pretrained("laion/larger_clap_general"),
+        "clap_model": ClapTextModelWithProjection.from_pretrained("laion/larger_clap_general").to(device).eval(),
+        "device": device,
+    })
+    siglip2_pre = v2.Compose([v2.Resize((512, 512), interpolation=v2.InterpolationMode.BICUBIC, antialias=True),
+                              v2.ToDtype(torch.float32, scale=True), v2.Normalize([0.5] * 3, [0.5] * 3)])
+    sync_pre = v2.Compose([v2.Resize(224, interpolation=v2.InterpolationMode.BICUBIC, antialias=True),
+                           v2.CenterCrop(224), v2.ToDtype(torch.float32, scale=True),
+                           v2.Normalize([0.5] * 3, [0.5] * 3)])
+
+    def extract_features(frames_8fps, frames_25fps, prompt, negative_prompt):
+        visual, audio_len = {}, None
+        if frames_8fps is not None:
+            x8 = torch.stack([siglip2_pre(f) for f in frames_8fps]).unsqueeze(0).to(device)
+            x25 = torch.stack([sync_pre(f) for f in frames_25fps]).unsqueeze(0).to(device)
+            visual["siglip2_feat"] = encode_video_with_siglip2(x8, deps)
+            visual["syncformer_feat"] = encode_video_with_sync(x25, deps)
+            audio_len = frames_25fps.shape[0] / 25.0
+        feats, _ = encode_text_feat([negative_prompt, prompt], deps)
+        return visual, {"text_feat": feats[1:], "uncond_text_feat": feats[:1]}, audio_len
+
+    out = dict(deps)
+    out["extract_features"] = extract_features
+    return out

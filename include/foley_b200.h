@@ -119,6 +119,11 @@ int64_t      foley_launch_count(const foley_engine* e);
  * (e.g. "audio", "v_cond", "vec"); returns the element count via n_out. */
 foley_status foley_debug_read(foley_engine* e, const char* what, float* dst, int64_t cap, int64_t* n_out);
 
+/* Reads and clears device debug words: out4[0] = code of the first pipeline wait that timed out (0 = none). */
+foley_status foley_debug_flags(uint32_t* out4);
+/* Runtime switches for tests / profiling: "cuda_graph" (0/1, default 1), "max_splits" (1..8, default 8). */
+foley_status foley_engine_set_option(foley_engine* e, const char* key, int64_t value);
+
 /* ---- low-level kernels exported for unit tests and micro-benchmarks --------------------------- */
 /* C[b,r,n] = sum_tap sum_k A[b, r+off0+tap*stride, k] * W[n, tap*K+k]; dtype bf16 -> tcgen05 kind::f16,
  * f32 -> kind::tf32.  mode: 0 bf16 out (+bias,+act), 1 SwiGLU pairs, 2 f32 partials (splits).  */
