@@ -110,7 +110,7 @@ def dit_param_specs(c):
 
 # DAC-VAE decoder hyper-parameters (utils.py:32-44 _DAC_KWARGS)
 DAC_CONFIG = dict(latent_dim=128, decoder_dim=2048, decoder_rates=(8, 5, 4, 3, 2), sample_rate=48000)
-DAC_TINY = dict(latent_dim=128, decoder_dim=256, decoder_rates=(8, 5, 4, 3, 2), sample_rate=48000)
+DAC_TINY = dict(latent_dim=128, decoder_dim=1024, decoder_rates=(8, 5, 4, 3, 2), sample_rate=48000)
 
 
 def dac_param_specs(d):
