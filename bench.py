@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""Benchmark of the denoise hot path (BASELINE.json): audio-seconds/sec and denoise-steps/sec at
+5 s / 50 Euler steps / CFG 4.5, synthetic conditions + seeded random weights of the named architecture.
+
+    python bench.py --gpus N --steps K --warmup W [--impl b200|reference] [--model xl|xxl] [--batch B]
+
+One bench "step" = one whole job of the hot path for the local batch: 50 x (CFG-pair DiT forward + CFG combine +
+Euler update) + one DAC-VAE decode.  `value` is measured with conditions / noise already resident in HBM;
+`e2e` goes through the public host API (sampling.denoise_process_with_generator, what the Sampler node calls)
+with pinned HOST buffers, H2D of conditions + noise and D2H of the waveforms inside the timed region.
+Multi-GPU: one process per GPU (torchrun), variations sharded across ranks (weak scaling: --batch per GPU), one
+NCCL broadcast of the condition embeddings and one gather of the decoded waveforms in the e2e leg.
+
+--impl reference times the reference's CPU path on the host cores.  The reference is Python and cannot travel
+to the GPU box, so this arm runs the oracle port (oracle/foley_oracle.py, fp32, all host threads) on a bounded
+sample of the same workload: one triple-stream block, one single-stream block and a short DAC decode at the
+benchmark's shapes, extrapolated linearly by block / step / frame counts (every block and step has identical
+shapes).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from tools import synthetic as SY  # noqa: E402
+
+# Algorithmic (reference-executed) TFLOP per Euler step for one CFG pair at 5 s (FlopCounterMode)
+STEP_TFLOP_5S = {"xxl": 3.8437, "xl": 2.1865}
+DAC_GFLOP_5S = 577.3
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def load_pkg(sub):
+    import __graft_entry__ as ge
+    return ge.load_pkg(sub)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_sample(model, batch, duration, n_steps, guidance, threads=None):
+    """Times the oracle port (fp32 CPU) on one triple block + one single block + embed/final + a short DAC decode at
+    the benchmark shapes and extrapolates to the whole job.  Returns (audio_s_per_s, steps_per_s, detail)."""
+    from oracle import foley_oracle as O   # checker / baseline only; never on the product path
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    c = SY.model_config(model)
+    L, Lv, S = SY.clip_lengths(duration)
+    B2 = batch * (2 if guidance > 1.0 else 1)
+    C, D, T = c["hidden_size"], c["head_dim"], 77
+    # one block's worth of weights (shapes only matter for timing); reuse for the extrapolated blocks
+    specs = [s for s in SY.dit_param_specs(c) if s[0].startswith(("triple_blocks.0.", "single_blocks.0."))]
+    sd = {n: torch.randn(sh) * 0.02 for n, sh, _ in specs}
+    p = O.Policy("fp32")
+    g = torch.Generator().manual_seed(0)
+    audio = torch.randn(B2, L, C, generator=g)
+    v_cond = torch.randn(B2, Lv, C, generator=g)
+    cond = torch.randn(B2, T, C, generator=g)
+    vec = torch.randn(B2, C, generator=g)
+    vec_tok = torch.randn(B2, L, C, generator=g)
+    a_pos, v_pos = O.interleaved_positions(L, Lv)
+    rope_av = (O.rope_tables(a_pos, D), O.rope_tables(v_pos, D))
+    rope_a, rope_v, rope_t = O.rope_tables(torch.arange(L), D), O.rope_tables(torch.arange(Lv), D), O.rope_tables(torch.arange(T), D)
+
+    def timed(fn, reps=2):
+        fn()  # warm-up
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps
+
+    with torch.inference_mode():
+        t_triple = timed(lambda: O.triple_block(p, sd, "triple_blocks.0.", c, audio, cond, v_cond, vec, rope_av, rope_a, rope_v, rope_t))
+        t_single = timed(lambda: O.single_block(p, sd, "single_blocks.0.", c, audio, vec_tok, rope_a))
+        dsd = SY.synth_dac_state_dict(SY.DAC_CONFIG, seed=3)
+        Ld = 10
+        z = torch.randn(1, 128, Ld, generator=g)
+        t_dac = timed(lambda: O.dac_decode(dsd, z), reps=1) * (L / Ld) * batch
+    t_step = c["depth_triple_blocks"] * t_triple + c["depth_single_blocks"] * t_single
+    t_job = n_steps * t_step + t_dac
+    detail = {"t_triple_block_s": t_triple, "t_single_block_s": t_single, "t_dac_decode_s": t_dac,
+              "t_euler_step_s": t_step, "t_job_s": t_job}
+    return batch * duration / t_job, 1.0 / t_step, detail
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count()
+    vals, steps_s = [], []
+    for i in range(args.warmup + args.steps):
+        v, s, detail = cpu_reference_sample(args.model, args.batch * args.gpus, args.duration, args.denoise_steps, args.cfg)
+        if i >= args.warmup:
+            vals.append(v)
+            steps_s.append(s)
+    value = sum(vals) / len(vals)
+    sample = ("oracle port (fp32 torch-CPU restatement of the reference), per bench step: 1 triple block + 1 single block "
+              "+ DAC decode of 10 latent frames at the benchmark shapes, extrapolated linearly to "
+              f"{args.denoise_steps} Euler steps x all blocks + full decode")
+    line = {
+        "impl": "reference", "metric": "audio_seconds_per_sec", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * args.batch * args.gpus * args.duration / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "denoise_steps_per_sec": sum(steps_s) / len(steps_s),
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args):
+    L, Lv, S = SY.clip_lengths(args.duration)
+    return {"workload": f"V2A {args.model} {args.duration:g}s@8fps synthetic, {args.denoise_steps} Euler steps, CFG {args.cfg:g}, "
+                        f"bf16, batch_size={args.batch}/GPU",
+            "model_size": args.model, "duration_s": args.duration, "denoise_steps": args.denoise_steps,
+            "cfg_scale": args.cfg, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+            "tokens": {"audio_L": L, "clip_Lv": Lv, "sync_S": S, "text_T": 77},
+            "parallelism": f"variations sharded x{args.gpus} (weights replicated)",
+            "l2_policy": "weights streamed per step are 5.8 GB (xl) / 10.3 GB (xxl) >> 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E, nodes, sampling, cfgmod = load_pkg("engine"), load_pkg("nodes"), load_pkg("sampling"), load_pkg("config")
+    peaks = load_peaks()
+
+    c = SY.model_config(args.model)
+    cfg = cfgmod.load_model_config(args.model)
+    L, Lv, S = SY.clip_lengths(args.duration)
+    B, U = args.batch, (2 if args.cfg > 1.0 else 1)
+    t0 = time.time()
+    sd = SY.synth_state_dict_cuda(SY.dit_param_specs(c), 0, dev, torch.bfloat16)   # same seed on every rank
+    eng = E.FoleyEngine(dict(cfg.model_config.model_kwargs), device=dev)
+    eng.load_state_dict(sd)
+    eng.finalize()
+    model = nodes.FoleyModel(eng, sd["empty_clip_feat"].cpu(), sd["empty_sync_feat"].cpu(), cfg, dtype=torch.bfloat16)
+    del sd
+    dsd = SY.synth_state_dict_cuda(SY.dac_param_specs(SY.DAC_CONFIG), 3, dev, torch.float32)
+    dac = nodes.FoleyDAC.from_state_dict(dsd, device=dev)
+    del dsd
+    torch.cuda.empty_cache()
+    setup_s = time.time() - t0
+
+    # synthetic conditions on rank 0's pinned host memory, one host noise draw for the global batch
+    feats = SY.synth_conditions(c, L, Lv, S, dtype=torch.bfloat16)
+    feats = {k: v.pin_memory() for k, v in feats.items()}
+    gen = torch.Generator(device="cpu").manual_seed(123)
+    noise_all = torch.randn((B * world, 128, L), generator=gen, dtype=torch.bfloat16).pin_memory()
+    sig = sampling.sigma_schedule(args.denoise_steps, 1.0)
+    stream = torch.cuda.Stream(device=dev)
+
+    def share_conditions(f_host):
+        """rank 0 -> all: ONE NCCL broadcast of the packed condition embeddings over NVLink."""
+        keys = ["siglip2_feat", "syncformer_feat", "text_feat", "uncond_text_feat"]
+        shapes = [tuple(f_host[k].shape) for k in keys]
+        n = sum(int(torch.tensor(s).prod()) for s in shapes)
+        flat = torch.empty(n, dtype=torch.bfloat16, device=dev)
+        if rank == 0:
+            off = 0
+            for k in keys:
+                m = f_host[k].numel()
+                flat[off:off + m].copy_(f_host[k].reshape(-1), non_blocking=True)
+                off += m
+        if world > 1:
+            dist.broadcast(flat, src=0)
+        out, off = {}, 0
+        for k, s in zip(keys, shapes):
+            m = int(torch.tensor(s).prod())
+            out[k] = flat[off:off + m].view(s)
+            off += m
+        return out
+
+    def cond_rows(f):
+        text = sampling._pad_or_trim_time(f["text_feat"], 77)
+        utext = sampling._pad_or_trim_time(f["uncond_text_feat"], 77)
+        if U == 2:
+            uclip = model.get_empty_clip_sequence(bs=1, len=Lv).to(dev)
+            usync = model.get_empty_sync_sequence(bs=1, len=S).to(dev)
+            return torch.cat([uclip, f["siglip2_feat"]]), torch.cat([usync, f["syncformer_feat"]]), torch.cat([utext, text])
+        return f["siglip2_feat"], f["syncformer_feat"], text
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.cuda.stream(stream):
+        # ================= device-resident leg (`value`) =================
+        f_dev = share_conditions(feats)
+        eng.set_conditions(*cond_rows(f_dev), L=L, batch=B)
+        noise_dev = noise_all[rank * B:(rank + 1) * B].to(dev).float()
+        for _ in range(args.warmup):
+            lat = eng.denoise(noise_dev, sig, args.cfg)
+            wav = dac.decode(lat)
+        torch.cuda.synchronize()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+        launches0 = eng.launch_count() + dac.engine.launch_count()
+        torch.cuda.synchronize()
+        ev[0].record()
+        for k in range(args.steps):
+            lat = eng.denoise(noise_dev, sig, args.cfg)
+            ev[2 * k + 1].record()
+            wav = dac.decode(lat)
+            ev[2 * k + 2].record()
+        torch.cuda.synchronize()
+        barrier()
+        launches = eng.launch_count() + dac.engine.launch_count() - launches0
+        total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
+        den_ms = max_over_ranks(sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)))
+        dac_ms = max_over_ranks(sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)))
+        if rank == 0:
+            sampler.stop_flag.set()
+            sampler.join(timeout=3)
+
+        # ================= end-to-end leg (`e2e`): public host API, host buffers =================
+        deps = cfgmod.AttributeDict({"dac_model": dac, "device": dev, "report_progress": False})
+        deps["foley_model"] = model
+        h2d = sum(v.numel() * v.element_size() for v in feats.values()) + B * 128 * L * 2
+        d2h = B * world * L * 960 * 4
+        gather_buf = [torch.empty(B, 1, L * 960, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+        def e2e_once():
+            f = share_conditions(feats)                       # H2D on rank 0 (+ NCCL broadcast)
+            visual = {"siglip2_feat": f["siglip2_feat"], "syncformer_feat": f["syncformer_feat"]}
+            text = {"text_feat": f["text_feat"], "uncond_text_feat": f["uncond_text_feat"]}
+            g = torch.Generator(device="cpu").manual_seed(123)
+            audio, _sr = sampling.denoise_process_with_generator(
+                visual, text, args.duration, deps, cfg, guidance_scale=args.cfg, num_inference_steps=args.denoise_steps,
+                batch_size=B * world, sampler="euler", generator=g, batch_slice=(rank * B, (rank + 1) * B))
+            if world > 1:
+                dist.gather(audio.contiguous(), gather_buf, dst=0)   # ONE gather of decoded waveforms
+                if rank == 0:
+                    return torch.cat(gather_buf).cpu()
+                return None
+            return audio.float().cpu()
+
+        for _ in range(max(1, args.warmup - 1)):
+            e2e_once()
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            out = e2e_once()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+
+        # ================= dominant kernel, timed alone (roofline) =================
+        roof = None
+        if rank == 0:
+            roof = time_dominant_gemm(eng, c, B * U, L, peaks)
+
+    if rank == 0:
+        gb = B * world
+        value = gb * args.duration * args.steps / (total_ms / 1e3)
+        steps_per_sec = args.denoise_steps * args.steps / (den_ms / 1e3)
+        e2e_val = gb * args.duration * args.steps / (e2e_ms / 1e3)
+        step_tflop = STEP_TFLOP_5S.get(args.model, 0) * B if abs(args.duration - 5.0) < 1e-6 and U == 2 else None
+        line = {
+            "metric": "audio_seconds_per_sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args),
+            "denoise_steps_per_sec": steps_per_sec, "sample_steps_per_sec": steps_per_sec * gb,
+            "ms_per_denoise_step": den_ms / args.steps / args.denoise_steps, "ms_dac_decode": dac_ms / args.steps,
+            "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": roof,
+            "setup_s": setup_s,
+        }
+        if step_tflop:
+            ach = step_tflop / (den_ms / args.steps / args.denoise_steps / 1e3)
+            line["step_roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                                     "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
+                                     "peak_source": peaks["_source"] + " sustained",
+                                     "flops": "algorithmic TFLOP per Euler step the reference executes (BASELINE.md §3)"}
+        if world == 1 and not args.no_cpu_baseline:
+            v, s, detail = cpu_reference_sample(args.model, B, args.duration, args.denoise_steps, args.cfg)
+            line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+                                    "denoise_steps_per_sec": s,
+                                    "sample": "oracle port fp32: 1 triple block + 1 single block + DAC decode of 10 frames at the "
+                                              "benchmark shapes, extrapolated linearly to the whole job", **detail}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def time_dominant_gemm(eng, c, B2, L, peaks):
+    """The single-stream ConvMLP w1/w3 k=3 conv GEMM (+SwiGLU epilogue): 37 % of the step's FLOPs (the three ConvMLP convs
+    together are 53 %).  Timed alone, back to back, with CUDA events on the launching stream."""
+    lib = eng.lib
+    i64, i32, vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p
+    lib.foley_gemm.argtypes = [vp, i32, i64, i64, i64, i64, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, i64,
+                               i64, i64, vp]
+    C, Hs = c["hidden_size"], c["mlp_hidden_single"]
+    dev = eng.device
+    a = torch.randn(B2, L, C, device=dev).bfloat16()
+    w = (torch.randn(2 * Hs, 3 * C, device=dev) * 0.02).bfloat16()
+    out = torch.empty(B2, L, Hs, device=dev, dtype=torch.bfloat16)
+    st = torch.cuda.current_stream(dev)
+
+    def launch():
+        s = lib.foley_gemm(a.data_ptr(), 0, B2, L, C, C, L * C, w.data_ptr(), 2 * Hs, 3, -1, 1, 1, 128, 1, 0, None,
+                           out.data_ptr(), Hs, L * Hs, 0, vp(st.cuda_stream))
+        assert s == 0, lib.foley_last_error()
+
+    for _ in range(5):
+        launch()
+    torch.cuda.synchronize()
+    iters = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    flops = 2.0 * B2 * L * 3 * C * 2 * Hs
+    ach = flops / (us * 1e-6) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    return {"kernel": "gemm_tcgen05_kernel<128,bf16> single-block ConvMLP w1|w3 conv(k=3)+SwiGLU", "bound": "tensor",
+            "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+            "peak_source": peaks["_source"] + " burst", "us_per_launch": us, "flops_per_launch": flops,
+            "traffic": traffic}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="xl", choices=["xl", "xxl", "small", "tiny"])
+    ap.add_argument("--batch", type=int, default=1, help="variations per GPU")
+    ap.add_argument("--duration", type=float, default=5.0)
+    ap.add_argument("--denoise-steps", type=int, default=50)
+    ap.add_argument("--cfg", type=float, default=4.5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -358,6 +358,15 @@ foley_status Engine::alloc_plan(int B, int U, int L, int Lv, int S, int T) {
     return FOLEY_OK;
 }
 
+// Tile width: 256-wide tiles halve the A-operand re-reads and the per-SM TMA ingress per MMA cycle (858 vs 526
+// TFLOP/s on the ConvMLP GEMM, profiles/r01_gemm_micro.txt); use them when N is wide enough that the grid still
+// covers most SMs, else 128.
+int Engine::pick_bn(int rows, int batch, int n) const {
+    const long long m_tiles = static_cast<long long>((rows + 127) / 128) * batch;
+    if (n % 256 == 0 && m_tiles * (n / 256) >= (num_sms * 3) / 4) return 256;
+    return 128;
+}
+
 int Engine::pick_splits(int rows, int batch, int n, int kblocks, int bn) const {
     const long long tiles = static_cast<long long>((n + bn - 1) / bn) * ((rows + 127) / 128) * batch;
     if (tiles * 10 >= static_cast<long long>(num_sms) * 7) return 1;
@@ -406,7 +415,7 @@ foley_status Engine::proj_combine(cudaStream_t st, const bf16* A, int rows, int 
     ca.split_stride = e.split_stride;
     ca.C = W.n;
     ca.rows_total = rows * batch;
-    combine_ln_mod_kernel<<<blocks_for(ca.rows_total, 4), 128, 0, st>>>(ca);
+    combine_ln_mod_kernel<<<ca.rows_total, ca.C / 4, 0, st>>>(ca);
     FOLEY_CUDA_OK(cudaGetLastError());
     ++launches;
     return FOLEY_OK;
@@ -594,7 +603,7 @@ foley_status Engine::step(cudaStream_t st) {
         GemmEpi e; e.mode = mode; e.act = act; e.out = out; e.ldo = ldo; e.bias = bias; return e;
     };
     auto launch_combine = [&](const CombineArgs& ca) -> foley_status {
-        combine_ln_mod_kernel<<<blocks_for(ca.rows_total, 4), 128, 0, st>>>(ca);
+        combine_ln_mod_kernel<<<ca.rows_total, ca.C / 4, 0, st>>>(ca);
         FOLEY_CUDA_OK(cudaGetLastError());
         ++launches;
         return FOLEY_OK;
@@ -639,7 +648,7 @@ foley_status Engine::step(cudaStream_t st) {
     for (int i = 0; i < NT; ++i) {
         const TripleW& w = triple[i];
         // -- joint self attention
-        ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.qkv[0], 0, 3 * C, bf(qkv_a, C3, w.qkv[0].b, 0), 1, 128));
+        ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.qkv[0], 0, 3 * C, bf(qkv_a, C3, w.qkv[0].b, 0), 1, pick_bn(L, B2, 3 * C)));
         ST_OK(gemm(st, h_v, Lv, B2, C, static_cast<long long>(Lv) * C, w.qkv[1], 0, 3 * C, bf(qkv_v, C3, w.qkv[1].b, 0), 1, 128));
         for (int s = 0; s < 2; ++s) {
             QkvArgs q;
@@ -692,7 +701,7 @@ foley_status Engine::step(cudaStream_t st) {
             ST_OK(proj_combine(st, attn_out, Lv, B2, C, jb, w.cross_proj[1], part_v, cv));
         }
         // -- MLPs
-        ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.fc1[0], 0, F, bf(mlp_a, F, w.fc1[0].b, ACT_GELU_TANH), 1, 128));
+        ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.fc1[0], 0, F, bf(mlp_a, F, w.fc1[0].b, ACT_GELU_TANH), 1, pick_bn(L, B2, F)));
         ST_OK(gemm(st, h_v, Lv, B2, C, static_cast<long long>(Lv) * C, w.fc1[1], 0, F, bf(mlp_v, F, w.fc1[1].b, ACT_GELU_TANH), 1, 128));
         {
             const bool last = i == NT - 1;
@@ -712,7 +721,7 @@ foley_status Engine::step(cudaStream_t st) {
     const long long sb = static_cast<long long>(L) * C, sh = static_cast<long long>(L) * 128;
     for (int j = 0; j < NS; ++j) {
         const SingleW& w = single[j];
-        ST_OK(gemm(st, h_a, L, B2, C, sb, w.qkv, 0, 3 * C, bf(qkv_a, C3, w.qkv.b, 0), 1, 128));
+        ST_OK(gemm(st, h_a, L, B2, C, sb, w.qkv, 0, 3 * C, bf(qkv_a, C3, w.qkv.b, 0), 1, pick_bn(L, B2, 3 * C)));
         {
             QkvArgs q;
             q.src = qkv_a; q.src_ld = 3 * C; q.n_parts = 3; q.H = H; q.L = L; q.rows_total = B2 * L;
@@ -733,7 +742,7 @@ foley_status Engine::step(cudaStream_t st) {
             ca.mod = smod(j); ca.shift_chunk = 3; ca.scale_chunk = 4; ca.rm = rm_a;
             ST_OK(proj_combine(st, attn_out, L, B2, C, sb, w.linear1, part_a, ca));
         }
-        ST_OK(gemm(st, h_a, L, B2, C, sb, w.w13, 0, 2 * Hs, bf(mlp_a, Hs, nullptr, 0, EPI_SWIGLU), 1, 128));
+        ST_OK(gemm(st, h_a, L, B2, C, sb, w.w13, 0, 2 * Hs, bf(mlp_a, Hs, nullptr, 0, EPI_SWIGLU), 1, pick_bn(L, B2, 2 * Hs)));
         {
             const bool last = j == NS - 1;
             CombineArgs ca;

@@ -1,6 +1,6 @@
 // Row-wise (HBM/L2-bound) kernels of the DiT step: everything between the tensor-core GEMMs.
-// One warp owns one token row (C <= 2048 channels kept in registers), so LayerNorm statistics are
-// warp-shuffle reductions and every global access is a coalesced 8/16-byte vector.
+// One CTA owns one token row (C/4 threads, one float4 each), LayerNorm statistics are shuffle + one
+// shared-memory hop, and every global access is a coalesced 8/16-byte vector.
 //
 // Rounding points follow the reference's CUDA-autocast dataflow (oracle/foley_oracle.py "cuda_bf16",
 // SURVEY.md Appendix B): fp32 LayerNorm, (1+scale) rounded to bf16, result rounded to bf16 for the next
@@ -9,8 +9,6 @@
 #include "ptx.cuh"
 
 namespace foley {
-
-constexpr int kMaxVecPerLane = 16;  // C <= 32 lanes * 16 * 4 = 2048
 
 // Where a row finds its modulation vectors (shift / scale / gate), all bf16:
 //   ptr = base + grp_or_trow * sample_stride + l * tok_stride + chunk * C
@@ -55,30 +53,6 @@ __device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, const float (&v)[
     *reinterpret_cast<uint2*>(p) = u;
 }
 
-// LayerNorm (no affine) of a register-resident row, two-pass in fp32 like ATen's CUDA kernel.
-template <int NV>
-__device__ __forceinline__ void row_layer_norm(float (&x)[NV][4], int nvec, int C, float eps) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-        if (i < nvec) s += (x[i][0] + x[i][1]) + (x[i][2] + x[i][3]);
-    const float mean = warp_sum(s) / C;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-        if (i < nvec) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const float d = x[i][j] - mean; q += d * d; }
-        }
-    const float rstd = rsqrtf(warp_sum(q) / C + eps);
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-        if (i < nvec) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) x[i][j] = (x[i][j] - mean) * rstd;
-        }
-}
-
 struct CombineArgs {
     // ---- residual update (skipped when partials == nullptr):
     //   y = bf16r(sum_s partials[s][row] + bias);  if gate: y = bf16r(y * gate);  x = x_src + y
@@ -102,92 +76,87 @@ struct CombineArgs {
     RowMap rm;
 };
 
-// grid: ceil(rows_total / 4) blocks of 128 threads; one warp per row.
-__global__ void __launch_bounds__(128) combine_ln_mod_kernel(const CombineArgs a) {
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= a.rows_total) return;
+// Block-wide sum for blocks of up to 16 warps: one __syncthreads per call (distinct scratch per call site).
+__device__ __forceinline__ float block_sum(float v, float* scratch /*[16]*/) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) scratch[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (i < nw) t += scratch[i];
+    return t;
+}
+
+// grid: one CTA per token row, C/4 threads, one float4 per thread: every access is a fully coalesced 16-byte
+// vector and a 500-row call still puts ~40 warps on every SM (the first version used one warp per row and was
+// latency-bound at 27 us per call, 30 % of the step; profiles/r01_launches_xl_v1.txt).
+__global__ void __launch_bounds__(512) combine_ln_mod_kernel(const CombineArgs a) {
+    __shared__ float red0[16], red1[16];
+    const int row = blockIdx.x;
     const int b = row / a.rm.L, l = row - b * a.rm.L;
     const int C = a.C;
-    const int nvec = C / 128;  // float4 vectors per lane (C is a multiple of 128)
-    float x[kMaxVecPerLane][4];
+    const int c = threadIdx.x * 4;
+    float x[4];
     float* xrow = a.x + static_cast<long long>(row) * C;
 
     if (a.x_init) {
         const int g = a.rm.grp_of_sample[b];
-        const __nv_bfloat16* src = a.x_init + (static_cast<long long>(a.rm.cond_of_grp[g]) * a.rm.L + l) * C;
-#pragma unroll
-        for (int i = 0; i < kMaxVecPerLane; ++i)
-            if (i < nvec) load_bf16x4(src + (i * 32 + lane) * 4, x[i]);
+        load_bf16x4(a.x_init + (static_cast<long long>(a.rm.cond_of_grp[g]) * a.rm.L + l) * C + c, x);
     } else {
-#pragma unroll
-        for (int i = 0; i < kMaxVecPerLane; ++i)
-            if (i < nvec) {
-                const float4 v = *reinterpret_cast<const float4*>(xrow + (i * 32 + lane) * 4);
-                x[i][0] = v.x; x[i][1] = v.y; x[i][2] = v.z; x[i][3] = v.w;
-            }
+        const float4 v = *reinterpret_cast<const float4*>(xrow + c);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
     }
 
     if (a.partials) {
-        const __nv_bfloat16* gate = a.gate.base ? mod_ptr(a.gate, a.rm, b, l, a.gate_chunk, C) : nullptr;
+        const float* pr = a.partials + static_cast<long long>(row) * C + c;
+        float4 acc = *reinterpret_cast<const float4*>(pr);
+        for (int s = 1; s < a.splits; ++s) {
+            const float4 p = *reinterpret_cast<const float4*>(pr + s * a.split_stride);
+            acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        }
+        float y[4] = {acc.x, acc.y, acc.z, acc.w};
+        if (a.bias) {
+            float bv[4];
+            load_bf16x4(a.bias + c, bv);
 #pragma unroll
-        for (int i = 0; i < kMaxVecPerLane; ++i)
-            if (i < nvec) {
-                const int c = (i * 32 + lane) * 4;
-                float4 acc = *reinterpret_cast<const float4*>(a.partials + static_cast<long long>(row) * C + c);
-                for (int s = 1; s < a.splits; ++s) {
-                    const float4 p = *reinterpret_cast<const float4*>(a.partials + s * a.split_stride +
-                                                                      static_cast<long long>(row) * C + c);
-                    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
-                }
-                float y[4] = {acc.x, acc.y, acc.z, acc.w};
-                if (a.bias) {
-                    float bv[4];
-                    load_bf16x4(a.bias + c, bv);
+            for (int j = 0; j < 4; ++j) y[j] += bv[j];
+        }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) y[j] += bv[j];
-                }
+        for (int j = 0; j < 4; ++j) y[j] = bf16_round(y[j]);
+        if (a.gate.base) {
+            float gv[4];
+            load_bf16x4(mod_ptr(a.gate, a.rm, b, l, a.gate_chunk, C) + c, gv);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) y[j] = bf16_round(y[j]);
-                if (gate) {
-                    float gv[4];
-                    load_bf16x4(gate + c, gv);
+            for (int j = 0; j < 4; ++j) y[j] = bf16_round(y[j] * gv[j]);
+        }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) y[j] = bf16_round(y[j] * gv[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    x[i][j] += y[j];
-                    if (a.round_x) x[i][j] = bf16_round(x[i][j]);
-                }
-            }
+        for (int j = 0; j < 4; ++j) {
+            x[j] += y[j];
+            if (a.round_x) x[j] = bf16_round(x[j]);
+        }
     }
-    if (a.partials || a.x_init) {
-#pragma unroll
-        for (int i = 0; i < kMaxVecPerLane; ++i)
-            if (i < nvec)
-                *reinterpret_cast<float4*>(xrow + (i * 32 + lane) * 4) = make_float4(x[i][0], x[i][1], x[i][2], x[i][3]);
-    }
+    if (a.partials || a.x_init) *reinterpret_cast<float4*>(xrow + c) = make_float4(x[0], x[1], x[2], x[3]);
 
     if (a.h) {
-        row_layer_norm<kMaxVecPerLane>(x, nvec, C, a.eps);
-        const __nv_bfloat16* sh = a.mod.base ? mod_ptr(a.mod, a.rm, b, l, a.shift_chunk, C) : nullptr;
-        const __nv_bfloat16* sc = a.mod.base ? mod_ptr(a.mod, a.rm, b, l, a.scale_chunk, C) : nullptr;
-        __nv_bfloat16* hrow = a.h + static_cast<long long>(row) * C;
+        // two-pass LayerNorm in fp32 (mean, then centred second moment), like ATen's CUDA kernel
+        const float mean = block_sum((x[0] + x[1]) + (x[2] + x[3]), red0) / C;
+        float q = 0.f;
 #pragma unroll
-        for (int i = 0; i < kMaxVecPerLane; ++i)
-            if (i < nvec) {
-                const int c = (i * 32 + lane) * 4;
-                float o[4] = {x[i][0], x[i][1], x[i][2], x[i][3]};
-                if (sh) {
-                    float sv[4], cv[4];
-                    load_bf16x4(sh + c, sv);
-                    load_bf16x4(sc + c, cv);
+        for (int j = 0; j < 4; ++j) { x[j] -= mean; q += x[j] * x[j]; }
+        const float rstd = rsqrtf(block_sum(q, red1) / C + a.eps);
+        float o[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = __fadd_rn(__fmul_rn(o[j], bf16_round(1.0f + cv[j])), sv[j]);
-                }
-                store_bf16x4(hrow + c, o);
-            }
+        for (int j = 0; j < 4; ++j) o[j] = x[j] * rstd;
+        if (a.mod.base) {
+            float sv[4], cv[4];
+            load_bf16x4(mod_ptr(a.mod, a.rm, b, l, a.shift_chunk, C) + c, sv);
+            load_bf16x4(mod_ptr(a.mod, a.rm, b, l, a.scale_chunk, C) + c, cv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = __fadd_rn(__fmul_rn(o[j], bf16_round(1.0f + cv[j])), sv[j]);
+        }
+        store_bf16x4(a.h + static_cast<long long>(row) * C + c, o);
     }
 }
 
