@@ -187,6 +187,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E, nodes, sampling, cfgmod = load_pkg("engine"), load_pkg("nodes"), load_pkg("sampling"), load_pkg("config")
+    par = load_pkg("parallel")
     peaks = load_peaks()
 
     c = SY.model_config(args.model)
@@ -214,26 +215,11 @@ def run_b200(args):
     sig = sampling.sigma_schedule(args.denoise_steps, 1.0)
     stream = torch.cuda.Stream(device=dev)
 
+    cond_shapes = [tuple(feats[k].shape) for k in par.COND_KEYS]
+
     def share_conditions(f_host):
-        """rank 0 -> all: ONE NCCL broadcast of the packed condition embeddings over NVLink."""
-        keys = ["siglip2_feat", "syncformer_feat", "text_feat", "uncond_text_feat"]
-        shapes = [tuple(f_host[k].shape) for k in keys]
-        n = sum(int(torch.tensor(s).prod()) for s in shapes)
-        flat = torch.empty(n, dtype=torch.bfloat16, device=dev)
-        if rank == 0:
-            off = 0
-            for k in keys:
-                m = f_host[k].numel()
-                flat[off:off + m].copy_(f_host[k].reshape(-1), non_blocking=True)
-                off += m
-        if world > 1:
-            dist.broadcast(flat, src=0)
-        out, off = {}, 0
-        for k, s in zip(keys, shapes):
-            m = int(torch.tensor(s).prod())
-            out[k] = flat[off:off + m].view(s)
-            off += m
-        return out
+        """rank 0 -> all: ONE broadcast of the packed condition embeddings (NCCL over NVLink when world > 1)."""
+        return par.broadcast_conditions(f_host if rank == 0 else None, cond_shapes, dev, src=0)
 
     def cond_rows(f):
         text = sampling._pad_or_trim_time(f["text_feat"], 77)
@@ -292,7 +278,6 @@ def run_b200(args):
         deps["foley_model"] = model
         h2d = sum(v.numel() * v.element_size() for v in feats.values()) + B * 128 * L * 2
         d2h = B * world * L * 960 * 4
-        gather_buf = [torch.empty(B, 1, L * 960, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
 
         def e2e_once():
             f = share_conditions(feats)                       # H2D on rank 0 (+ NCCL broadcast)
@@ -302,12 +287,8 @@ def run_b200(args):
             audio, _sr = sampling.denoise_process_with_generator(
                 visual, text, args.duration, deps, cfg, guidance_scale=args.cfg, num_inference_steps=args.denoise_steps,
                 batch_size=B * world, sampler="euler", generator=g, batch_slice=(rank * B, (rank + 1) * B))
-            if world > 1:
-                dist.gather(audio.contiguous(), gather_buf, dst=0)   # ONE gather of decoded waveforms
-                if rank == 0:
-                    return torch.cat(gather_buf).cpu()
-                return None
-            return audio.float().cpu()
+            full = par.gather_waveforms(audio.float(), B * world, dst=0)   # ONE gather of decoded waveforms
+            return full.cpu() if full is not None else None
 
         for _ in range(max(1, args.warmup - 1)):
             e2e_once()
