@@ -360,8 +360,12 @@ def time_dominant_gemm(eng, c, B2, L, peaks):
     out = torch.empty(B2, L, Hs, device=dev, dtype=torch.bfloat16)
     st = torch.cuda.current_stream(dev)
 
+    # same tile-width rule as Engine::pick_bn
+    m_tiles = ((L + 127) // 128) * B2
+    bn = 256 if (2 * Hs) % 256 == 0 and m_tiles * (2 * Hs // 256) >= (148 * 3) // 4 else 128
+
     def launch():
-        s = lib.foley_gemm(a.data_ptr(), 0, B2, L, C, C, L * C, w.data_ptr(), 2 * Hs, 3, -1, 1, 1, 128, 1, 0, None,
+        s = lib.foley_gemm(a.data_ptr(), 0, B2, L, C, C, L * C, w.data_ptr(), 2 * Hs, 3, -1, 1, 1, bn, 1, 0, None,
                            out.data_ptr(), Hs, L * Hs, 0, vp(st.cuda_stream))
         assert s == 0, lib.foley_last_error()
 
@@ -385,7 +389,7 @@ def time_dominant_gemm(eng, c, B2, L, peaks):
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    return {"kernel": "gemm_tcgen05_kernel<128,bf16> single-block ConvMLP w1|w3 conv(k=3)+SwiGLU", "bound": "tensor",
+    return {"kernel": f"gemm_tcgen05_kernel<{bn},bf16> single-block ConvMLP w1|w3 conv(k=3)+SwiGLU", "bound": "tensor",
             "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
             "peak_source": peaks["_source"] + " burst", "us_per_launch": us, "flops_per_launch": flops,
             "traffic": traffic}
