@@ -64,6 +64,8 @@ __device__ __forceinline__ void load_tile(uint32_t smem_base, const __nv_bfloat1
 }
 
 __global__ void __launch_bounds__(128) attention_kernel(const AttnArgs a) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(128) uint8_t att_smem[];
     const uint32_t sQ = smem_u32(att_smem);
     const uint32_t sK = sQ + ATT_BM * ATT_D * 2;

@@ -415,8 +415,7 @@ foley_status Engine::proj_combine(cudaStream_t st, const bf16* A, int rows, int 
     ca.split_stride = e.split_stride;
     ca.C = W.n;
     ca.rows_total = rows * batch;
-    combine_ln_mod_kernel<<<ca.rows_total, ca.C / 4, 0, st>>>(ca);
-    FOLEY_CUDA_OK(cudaGetLastError());
+    FOLEY_CUDA_OK(launch_k(combine_ln_mod_kernel, dim3(ca.rows_total), dim3(ca.C / 4), 0, st, ca));
     ++launches;
     return FOLEY_OK;
 }
@@ -522,7 +521,7 @@ foley_status Engine::set_conditions(const void* clip, const void* sync, const vo
         q.part[0].norm_w = triple[i].text_k_norm; q.part[0].src_col = i * 2 * C;
         q.part[1] = q.part[0];
         q.part[1].dst = text_v + i * blk; q.part[1].norm_w = nullptr; q.part[1].src_col = i * 2 * C + C;
-        qk_norm_rope_kernel<<<blocks_for(static_cast<long long>(q.rows_total) * 2 * H, 4), 128, 0, st>>>(q);
+        FOLEY_CUDA_OK(launch_k(qk_norm_rope_kernel, dim3(blocks_for(static_cast<long long>(q.rows_total) * 2 * H, 4)), dim3(128), 0, st, q));
         ++launches;
     }
     // ---- visual branch (hifi_foley.py:770)
@@ -603,8 +602,7 @@ foley_status Engine::step(cudaStream_t st) {
         GemmEpi e; e.mode = mode; e.act = act; e.out = out; e.ldo = ldo; e.bias = bias; return e;
     };
     auto launch_combine = [&](const CombineArgs& ca) -> foley_status {
-        combine_ln_mod_kernel<<<ca.rows_total, ca.C / 4, 0, st>>>(ca);
-        FOLEY_CUDA_OK(cudaGetLastError());
+        FOLEY_CUDA_OK(launch_k(combine_ln_mod_kernel, dim3(ca.rows_total), dim3(ca.C / 4), 0, st, ca));
         ++launches;
         return FOLEY_OK;
     };
@@ -619,8 +617,7 @@ foley_status Engine::step(cudaStream_t st) {
         a.grp_of_sample = cross ? grp_of_sample : nullptr;
         a.scale_log2 = 1.4426950408889634f / sqrtf(128.0f);
         dim3 grid((Sq + ATT_BM - 1) / ATT_BM, H, B2);
-        attention_kernel<<<grid, 128, ATT_SMEM, st>>>(a);
-        FOLEY_CUDA_OK(cudaGetLastError());
+        FOLEY_CUDA_OK(launch_k(attention_kernel, grid, dim3(128), ATT_SMEM, st, a));
         ++launches;
         return FOLEY_OK;
     };
@@ -628,7 +625,8 @@ foley_status Engine::step(cudaStream_t st) {
     // ---- single-block modulations for this step: x-independent, one GEMM for all NS blocks
     {
         const long long n4 = static_cast<long long>(G) * L * C / 4;
-        vectok_silu_kernel<<<blocks_for(n4, 256), 256, 0, st>>>(a_sync, vec_all, cond_of_grp, trow_of_grp, G, L, C, vectok_act);
+        FOLEY_CUDA_OK(launch_k(vectok_silu_kernel, dim3(blocks_for(n4, 256)), dim3(256), 0, st, a_sync, vec_all, cond_of_grp,
+                               trow_of_grp, G, L, C, vectok_act));
         ++launches;
         ST_OK(gemm(st, vectok_act, G * L, 1, C, 0, mod_single_all, 0, NS * 6 * C,
                    bf(mod_single, ms_tok, mod_single_all.b, 0), 1, 256));
@@ -661,7 +659,7 @@ foley_status Engine::step(cudaStream_t st) {
                 q.part[pz].dst = dsts[pz]; q.part[pz].dst_batch_stride = jb; q.part[pz].dst_head_stride = jh;
                 q.part[pz].seq_offset = s == 0 ? Lv : 0; q.part[pz].norm_w = norms[pz]; q.part[pz].src_col = pz * C;
             }
-            qk_norm_rope_kernel<<<blocks_for(static_cast<long long>(q.rows_total) * 3 * H, 4), 128, 0, st>>>(q);
+            FOLEY_CUDA_OK(launch_k(qk_norm_rope_kernel, dim3(blocks_for(static_cast<long long>(q.rows_total) * 3 * H, 4)), dim3(128), 0, st, q));
             ++launches;
         }
         ST_OK(attn(Qj, Kj, Vj, Sj, Sj, jb, jh, false));
@@ -684,7 +682,7 @@ foley_status Engine::step(cudaStream_t st) {
             q.rows_total = B2 * q.L; q.norm_kind = 0; q.eps = 1e-6f; q.cos = rope_plain_cos; q.sin = rope_plain_sin;
             q.part[0].dst = Qj; q.part[0].dst_batch_stride = jb; q.part[0].dst_head_stride = jh;
             q.part[0].seq_offset = s == 0 ? Lv : 0; q.part[0].norm_w = w.cross_q_norm[s]; q.part[0].src_col = 0;
-            qk_norm_rope_kernel<<<blocks_for(static_cast<long long>(q.rows_total) * H, 4), 128, 0, st>>>(q);
+            FOLEY_CUDA_OK(launch_k(qk_norm_rope_kernel, dim3(blocks_for(static_cast<long long>(q.rows_total) * H, 4)), dim3(128), 0, st, q));
             ++launches;
         }
         {
@@ -732,7 +730,7 @@ foley_status Engine::step(cudaStream_t st) {
                 q.part[pz].dst = dsts[pz]; q.part[pz].dst_batch_stride = sb; q.part[pz].dst_head_stride = sh;
                 q.part[pz].seq_offset = 0; q.part[pz].norm_w = norms[pz]; q.part[pz].src_col = pz * C;
             }
-            qk_norm_rope_kernel<<<blocks_for(static_cast<long long>(q.rows_total) * 3 * H, 4), 128, 0, st>>>(q);
+            FOLEY_CUDA_OK(launch_k(qk_norm_rope_kernel, dim3(blocks_for(static_cast<long long>(q.rows_total) * 3 * H, 4)), dim3(128), 0, st, q));
             ++launches;
         }
         ST_OK(attn(Qj, Kj, Vj, L, L, sb, sh, false));
@@ -793,8 +791,9 @@ foley_status Engine::denoise(float* latents, const float* sigmas, int n_steps, f
 
     auto body = [&]() -> foley_status {
         ST_OK(step(st));
-        cfg_euler_kernel<<<grid, blk, 0, st>>>(y_out, lat_dev, x_in, p.B, p.U, LAT, p.L, guidance, sigmas_dev, step_dev);
-        advance_step_kernel<<<1, 32, 0, st>>>(step_dev, trow_of_grp, cur_G);
+        FOLEY_CUDA_OK(launch_k(cfg_euler_kernel, grid, blk, 0, st, y_out, lat_dev, x_in, p.B, p.U, LAT, p.L, guidance,
+                               sigmas_dev, step_dev));
+        FOLEY_CUDA_OK(launch_k(advance_step_kernel, dim3(1), dim3(32), 0, st, step_dev, trow_of_grp, cur_G));
         launches += 2;
         FOLEY_CUDA_OK(cudaGetLastError());
         return FOLEY_OK;

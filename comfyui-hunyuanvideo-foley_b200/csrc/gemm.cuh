@@ -49,6 +49,8 @@ struct GemmArgs {
     int tap_stride;  // A row offset increment per tap
     int splits;      // K splits (gridDim.z); the taps*kb_per_tap k-blocks are divided evenly
     int dbg_stop;    // bring-up aid: 1 = setup only, 2 = TMA only, 3 = TMA+MMA, 0 = full kernel
+    int prefetch_b;  // L2 prefetch distance of the weight operand in k-blocks (0 = off)
+    int pf_mod;      // CTAs with blockIdx.x % pf_mod == 0 issue the prefetch (m-tiles sharing a weight column)
     GemmEpi epi;
 };
 
@@ -105,12 +107,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const int kb_end = static_cast<int>((static_cast<long long>(kb_total) * (split + 1)) / g.splits);
     const int num_kb = kb_end - kb_begin;
 
+    // Thread-block cluster (cx along the m-tile axis, cy along the n-tile axis; 1x1 when launched without one):
+    // CTAs of a cluster column share the A tile, CTAs of a cluster row share the B tile.  Each CTA loads a 1/cy
+    // slice of A and a 1/cx slice of B and multicasts it, so a tile crosses the L2 -> GPC fabric once per cluster
+    // instead of once per CTA (the un-clustered kernel saturates at ~5.3 KB/cycle of chip-wide SM ingress).
+    const uint32_t cx = cluster_nctaid_x(), cy = cluster_nctaid_y();
+    const uint32_t rx = cluster_ctaid_x(), ry = cluster_ctaid_y();
+    const bool clustered = cx * cy > 1;
+    uint32_t a_mask = 0, b_mask = 0;
+    for (uint32_t j = 0; j < cy; ++j) a_mask |= 1u << (rx + j * cx);
+    for (uint32_t i = 0; i < cx; ++i) b_mask |= 1u << (i + ry * cx);
+    const int a_rows = Cfg::BM / static_cast<int>(cy), b_rows = BN / static_cast<int>(cx);
+
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
         tma_prefetch_desc(&tm_b);
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], cx + cy - 1);   // one release per CTA that multicasts into this CTA's stage
         }
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
@@ -119,6 +133,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (clustered) cluster_sync_all();   // peers' barriers must be initialised before anything is multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -127,17 +142,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     } else if (warp == 0) {
         // ------------------------------------------------------------- TMA producer
         if (lane == 0) {
-            for (int i = 0; i < num_kb; ++i) {
+            auto load_b = [&](int i) {
                 const int s = i % Cfg::STAGES;
-                const uint32_t ph = (i / Cfg::STAGES) & 1;
-                if (!mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + i)) break;
+                const int kb = kb_begin + i;
+                mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                if (cx > 1)
+                    tma_load_3d_mc(smem_b + s * Cfg::B_BYTES + rx * b_rows * Cfg::BK_BYTES, &tm_b, &full_bar[s],
+                                   kb * Cfg::BK, n0 + rx * b_rows, 0, static_cast<uint16_t>(b_mask));
+                else
+                    tma_load_3d(smem_b + s * Cfg::B_BYTES, &tm_b, &full_bar[s], kb * Cfg::BK, n0, 0);  // rank-3 map
+            };
+            auto load_a = [&](int i) {
+                const int s = i % Cfg::STAGES;
                 const int kb = kb_begin + i;
                 const int tap = kb / g.kb_per_tap;
                 const int kcol = (kb - tap * g.kb_per_tap) * Cfg::BK;
-                mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                tma_load_3d(smem_a + s * Cfg::A_BYTES, &tm_a, &full_bar[s], kcol,
-                            m0 + g.tap_off0 + tap * g.tap_stride, batch);
-                tma_load_3d(smem_b + s * Cfg::B_BYTES, &tm_b, &full_bar[s], kb * Cfg::BK, n0, 0);  // rank-3 map, batch 0
+                const int arow = m0 + g.tap_off0 + tap * g.tap_stride;
+                if (cy > 1)
+                    tma_load_3d_mc(smem_a + s * Cfg::A_BYTES + ry * a_rows * Cfg::BK_BYTES, &tm_a, &full_bar[s], kcol,
+                                   arow + ry * a_rows, batch, static_cast<uint16_t>(a_mask));
+                else
+                    tma_load_3d(smem_a + s * Cfg::A_BYTES, &tm_a, &full_bar[s], kcol, arow, batch);
+            };
+            // Weights do not depend on the previous kernel: fill the ring with B tiles before waiting on it
+            // (programmatic dependent launch), so the weight stream's HBM latency hides under the predecessor.
+            const int pre = num_kb < Cfg::STAGES ? num_kb : Cfg::STAGES;
+            for (int i = 0; i < pre; ++i) load_b(i);
+            pdl_wait();
+            for (int i = 0; i < num_kb; ++i) {
+                if (i >= pre) {
+                    const int s = i % Cfg::STAGES;
+                    const uint32_t ph = (i / Cfg::STAGES) & 1;
+                    if (!mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + i)) break;
+                    load_b(i);
+                }
+                load_a(i);
             }
         }
     } else if (warp == 1) {
@@ -160,7 +199,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     else
                         umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0);
                 }
-                umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+                // free the stage once these MMAs retire — in every CTA that writes into it
+                if (clustered) umma_commit_mc(&empty_bar[s], static_cast<uint16_t>(a_mask | b_mask));
+                else umma_commit(&empty_bar[s]);
             }
             if (g.dbg_stop == 2) mbar_arrive(tmem_full_bar);
             else umma_commit(tmem_full_bar);  // accumulator complete
@@ -169,7 +210,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // ------------------------------------------------------------- epilogue warps (2..5)
         const int q = warp & 3;              // TMEM lane quarter this warp may access
         const int r = m0 + q * 32 + lane;    // output row within the sample
+        pdl_wait();                          // outputs may alias buffers the predecessor still reads
         const bool acc_ok = mbar_wait(tmem_full_bar, 0, 0x300);
+        pdl_trigger();                       // mainloop done: the next kernel may start its prologue
         tc_fence_after();
         const GemmEpi& e = g.epi;
         const bool row_ok = r < g.rows;
@@ -283,6 +326,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         tc_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
+    if (clustered) cluster_sync_all();   // no CTA may exit while peers can still signal its barriers
 }
 
 }  // namespace foley

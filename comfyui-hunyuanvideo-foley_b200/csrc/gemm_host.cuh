@@ -2,6 +2,7 @@
 // runtime so the library has no link-time dependency on libcuda) and the launcher.
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -73,6 +74,60 @@ inline bool encode_operand_map(CUtensorMap* out, const Operand& t, int box_rows,
     return true;
 }
 
+// Programmatic dependent launch for every engine kernel (FOLEY_PDL=0 disables).
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FOLEY_PDL");
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
+}
+
+// Launch helper for the non-GEMM kernels of the step: same stream order, plus the programmatic-serialization
+// attribute so a kernel's launch latency and prologue overlap its predecessor's tail.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+inline int default_prefetch_distance() {
+    static int v = -2;
+    if (v == -2) {
+        const char* e = getenv("FOLEY_GEMM_PREFETCH");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+// Default cluster policy (override: FOLEY_GEMM_CLUSTER="XxY"): 2 along m when the m-tile count is even, 2 along n
+// when there are at least two n-tiles.
+inline void cluster_shape_for(long long m_tiles, long long n_tiles, int want_x, int want_y, int* cx, int* cy) {
+    static int env_x = -1, env_y = -1;
+    if (env_x < 0) {
+        env_x = 1; env_y = 1;
+        if (const char* e = getenv("FOLEY_GEMM_CLUSTER")) {
+            int a = 0, b = 0;
+            if (sscanf(e, "%dx%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= 8) { env_x = a; env_y = b; }
+        }
+    }
+    int x = want_x > 0 ? want_x : env_x, y = want_y > 0 ? want_y : env_y;
+    while (x > 1 && m_tiles % x != 0) x /= 2;
+    while (y > 1 && n_tiles < y) y /= 2;
+    if ((x & (x - 1)) || (y & (y - 1))) { x = 1; y = 1; }   // slices must divide the tile evenly
+    *cx = x; *cy = y;
+}
+
 struct GemmLaunch {
     Operand a;                 // activations [batch, rows, K]
     const void* w = nullptr;   // weights [N, taps*K], K-major, same dtype as a
@@ -81,13 +136,15 @@ struct GemmLaunch {
     int splits = 1;
     int bn = 128;              // tile width: 64, 128 or 256
     int dbg_stop = 0;
+    int prefetch_b = -1;       // -1: default distance
+    int cluster_x = 0, cluster_y = 0;  // 0: default policy
     long long out_rows = 0;    // output rows per sample (0 -> a.rows); may exceed a.rows (halo rows read as zero)
     GemmEpi epi;
 };
 
 template <int BN, bool kTF32>
 inline cudaError_t launch_gemm_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& args,
-                                    dim3 grid, cudaStream_t stream) {
+                                    dim3 grid, cudaStream_t stream, int cx = 1, int cy = 1) {
     using Cfg = GemmCfg<BN, kTF32>;
     auto kern = gemm_tcgen05_kernel<BN, kTF32>;
     static bool attr_set = false;
@@ -100,8 +157,28 @@ inline cudaError_t launch_gemm_inst(const CUtensorMap& ma, const CUtensorMap& mb
             attr_set = true;
         }
     }
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, args);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cx * cy > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cx;
+        attr[na].val.clusterDim.y = cy;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kern, ma, mb, args);
 }
 
 // Opts every instantiation into its dynamic shared-memory size up front (must not happen lazily inside a
@@ -129,12 +206,18 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
     const int bk = tf32 ? 32 : 64;
     if (L.a.k % bk != 0) { if (err) *err = "GEMM K must be a multiple of the 128-byte k-block"; return false; }
     if (L.n % 16 != 0) { if (err) *err = "GEMM N must be a multiple of 16"; return false; }
+    // cluster shape: pairs of m-tiles share B, pairs of n-tiles share A (see gemm.cuh)
+    const long long out_rows_c = L.out_rows > 0 ? L.out_rows : L.a.rows;
+    const long long mt = ((out_rows_c + 127) / 128) * (L.a.batch > 0 ? L.a.batch : 1);
+    const long long nt = (L.n + L.bn - 1) / L.bn;
+    int cx = 1, cy = 1;
+    cluster_shape_for(mt, nt, L.cluster_x, L.cluster_y, &cx, &cy);
     CUtensorMap ma, mb;
-    if (!encode_operand_map(&ma, L.a, 128, err)) return false;
+    if (!encode_operand_map(&ma, L.a, 128 / cy, err)) return false;
     Operand wb;
     wb.ptr = L.w; wb.dtype = L.a.dtype; wb.k = L.a.k * L.taps; wb.rows = L.n; wb.batch = 1;
     wb.ld = wb.k; wb.batch_stride = wb.k * wb.rows;
-    if (!encode_operand_map(&mb, wb, L.bn, err)) return false;
+    if (!encode_operand_map(&mb, wb, L.bn / cx, err)) return false;
 
     GemmArgs args;
     const long long out_rows = L.out_rows > 0 ? L.out_rows : L.a.rows;
@@ -147,19 +230,21 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
     args.splits = L.splits < 1 ? 1 : L.splits;
     args.epi = L.epi;
     args.dbg_stop = L.dbg_stop;
+    args.prefetch_b = L.prefetch_b < 0 ? default_prefetch_distance() : L.prefetch_b;
+    args.pf_mod = 1;
     const int m_tiles = static_cast<int>((out_rows + 127) / 128);
     dim3 grid(static_cast<unsigned>(m_tiles * (L.a.batch > 0 ? L.a.batch : 1)),
-              static_cast<unsigned>((L.n + L.bn - 1) / L.bn), static_cast<unsigned>(args.splits));
+              static_cast<unsigned>(((nt + cy - 1) / cy) * cy), static_cast<unsigned>(args.splits));
     cudaError_t e = cudaSuccess;
     if (!tf32) {
-        if (L.bn == 64) e = launch_gemm_inst<64, false>(ma, mb, args, grid, stream);
-        else if (L.bn == 128) e = launch_gemm_inst<128, false>(ma, mb, args, grid, stream);
-        else if (L.bn == 256) e = launch_gemm_inst<256, false>(ma, mb, args, grid, stream);
+        if (L.bn == 64) e = launch_gemm_inst<64, false>(ma, mb, args, grid, stream, cx, cy);
+        else if (L.bn == 128) e = launch_gemm_inst<128, false>(ma, mb, args, grid, stream, cx, cy);
+        else if (L.bn == 256) e = launch_gemm_inst<256, false>(ma, mb, args, grid, stream, cx, cy);
         else { if (err) *err = "unsupported BN"; return false; }
     } else {
-        if (L.bn == 64) e = launch_gemm_inst<64, true>(ma, mb, args, grid, stream);
-        else if (L.bn == 128) e = launch_gemm_inst<128, true>(ma, mb, args, grid, stream);
-        else if (L.bn == 256) e = launch_gemm_inst<256, true>(ma, mb, args, grid, stream);
+        if (L.bn == 64) e = launch_gemm_inst<64, true>(ma, mb, args, grid, stream, cx, cy);
+        else if (L.bn == 128) e = launch_gemm_inst<128, true>(ma, mb, args, grid, stream, cx, cy);
+        else if (L.bn == 256) e = launch_gemm_inst<256, true>(ma, mb, args, grid, stream, cx, cy);
         else { if (err) *err = "unsupported BN"; return false; }
     }
     if (e != cudaSuccess) {

@@ -93,6 +93,8 @@ __device__ __forceinline__ float block_sum(float v, float* scratch /*[16]*/) {
 // vector and a 500-row call still puts ~40 warps on every SM (the first version used one warp per row and was
 // latency-bound at 27 us per call, 30 % of the step; profiles/r01_launches_xl_v1.txt).
 __global__ void __launch_bounds__(512) combine_ln_mod_kernel(const CombineArgs a) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red0[16], red1[16];
     const int row = blockIdx.x;
     const int b = row / a.rm.L, l = row - b * a.rm.L;
@@ -190,6 +192,8 @@ struct QkvArgs {
 };
 
 __global__ void __launch_bounds__(128) qk_norm_rope_kernel(const QkvArgs a) {
+    pdl_wait();
+    pdl_trigger();
     const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int per_row = a.n_parts * a.H;
@@ -252,6 +256,8 @@ __global__ void silu_bf16_kernel(const __nv_bfloat16* in, __nv_bfloat16* out, lo
 // followed by ModulateDiT's SiLU on the fp32 per-token condition)
 __global__ void vectok_silu_kernel(const __nv_bfloat16* a_sync, const __nv_bfloat16* vec, const int* cond_of_grp,
                                    const int* trow_of_grp, int G, int L, int C, __nv_bfloat16* out) {
+    pdl_wait();
+    pdl_trigger();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long n4 = static_cast<long long>(G) * L * C / 4;
     if (i >= n4) return;
@@ -297,6 +303,8 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* in, const int* idx, int 
 
 // latents fp32 [B, ch, L] -> model input bf16 [B2, L, ch] for every group copy (utils.py:205,223)
 __global__ void latents_to_tokens_kernel(const float* lat, int B, int n_rep, int ch, int L, __nv_bfloat16* out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -316,6 +324,8 @@ __global__ void latents_to_tokens_kernel(const float* lat, int B, int n_rep, int
 
 // model output bf16 [B2, L, ch] -> fp32 [B2, ch, L]   (unpatchify1d, hifi_foley.py:926-936)
 __global__ void tokens_to_channels_kernel(const __nv_bfloat16* y, int B2, int ch, int L, float* out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -334,6 +344,8 @@ __global__ void tokens_to_channels_kernel(const __nv_bfloat16* y, int B2, int ch
 // step_state: [0] = step index (incremented by thread 0 of block 0 after use), sigmas on device.
 __global__ void cfg_euler_kernel(const __nv_bfloat16* y, float* lat, __nv_bfloat16* x_next, int B, int n_cond,
                                  int ch, int L, float guidance, const float* sigmas, const int* step_ptr) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
     const int step = *step_ptr;
@@ -376,6 +388,8 @@ __global__ void cfg_euler_kernel(const __nv_bfloat16* y, float* lat, __nv_bfloat
 // Advances the device-side step counter and the per-group timestep rows (one tiny launch per step so the
 // whole step can be replayed as one CUDA graph).
 __global__ void advance_step_kernel(int* step_ptr, int* trow_of_grp, int G) {
+    pdl_wait();
+    pdl_trigger();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const int s = *step_ptr + 1;
         *step_ptr = s;
