@@ -24,6 +24,9 @@ Engine::~Engine() {
     cudaSetDevice(device);
     if (step_graph) cudaGraphExecDestroy(step_graph);
     if (own_stream) cudaStreamDestroy(own_stream);
+    if (side_stream) cudaStreamDestroy(side_stream);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     free_plan();
     for (auto& kv : raw)
         if (kv.second.dev) cudaFree(kv.second.dev);
@@ -63,6 +66,9 @@ foley_status Engine::create(const foley_config* c, int dev) {
     if (prop.major != 10) return fail(FOLEY_ERR_UNSUPPORTED, "foley_b200 requires an sm_100 (Blackwell B200) device");
     num_sms = prop.multiProcessorCount;
     FOLEY_CUDA_OK(cudaStreamCreate(&own_stream));
+    FOLEY_CUDA_OK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     {
         std::string err;
         if (!gemm_init_attributes(&err)) return fail(FOLEY_ERR_CUDA, err);
@@ -363,7 +369,7 @@ foley_status Engine::alloc_plan(int B, int U, int L, int Lv, int S, int T) {
 // covers most SMs, else 128.
 int Engine::pick_bn(int rows, int batch, int n) const {
     const long long m_tiles = static_cast<long long>((rows + 127) / 128) * batch;
-    if (n % 256 == 0 && m_tiles * (n / 256) >= (num_sms * 3) / 4) return 256;
+    if (n % 256 == 0 && m_tiles * (n / 256) >= (num_sms * 11) / 20) return 256;
     return 128;
 }
 
@@ -601,11 +607,6 @@ foley_status Engine::step(cudaStream_t st) {
     auto bf = [&](bf16* out, long long ldo, const bf16* bias, int act, int mode = EPI_BF16) {
         GemmEpi e; e.mode = mode; e.act = act; e.out = out; e.ldo = ldo; e.bias = bias; return e;
     };
-    auto launch_combine = [&](const CombineArgs& ca) -> foley_status {
-        FOLEY_CUDA_OK(launch_k(combine_ln_mod_kernel, dim3(ca.rows_total), dim3(ca.C / 4), 0, st, ca));
-        ++launches;
-        return FOLEY_OK;
-    };
     auto attn = [&](const bf16* q, const bf16* k, const bf16* v, int Sq, int Sk, long long kv_bs, long long kv_hs,
                     bool cross) -> foley_status {
         AttnArgs a;
@@ -631,23 +632,49 @@ foley_status Engine::step(cudaStream_t st) {
         ST_OK(gemm(st, vectok_act, G * L, 1, C, 0, mod_single_all, 0, NS * 6 * C,
                    bf(mod_single, ms_tok, mod_single_all.b, 0), 1, 256));
     }
+    // The visual stream (B2*Lv = 80 rows at 5 s) is pure launch/latency overhead next to the audio stream: run it on a
+    // side stream (a parallel branch of the captured graph) and meet only at the two attention calls of a block.
+    cudaStream_t sv = side_stream;
+    auto fork = [&]() -> foley_status {
+        FOLEY_CUDA_OK(cudaEventRecord(ev_fork, st));
+        FOLEY_CUDA_OK(cudaStreamWaitEvent(sv, ev_fork, 0));
+        return FOLEY_OK;
+    };
+    auto join = [&]() -> foley_status {
+        FOLEY_CUDA_OK(cudaEventRecord(ev_join, sv));
+        FOLEY_CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
+        return FOLEY_OK;
+    };
+    auto combine_on = [&](cudaStream_t s_, const CombineArgs& ca) -> foley_status {
+        FOLEY_CUDA_OK(launch_k(combine_ln_mod_kernel, dim3(ca.rows_total), dim3(ca.C / 4), 0, s_, ca));
+        ++launches;
+        return FOLEY_OK;
+    };
+    auto qknorm_on = [&](cudaStream_t s_, const QkvArgs& q) -> foley_status {
+        FOLEY_CUDA_OK(launch_k(qk_norm_rope_kernel, dim3(blocks_for(static_cast<long long>(q.rows_total) * q.n_parts * H, 4)),
+                               dim3(128), 0, s_, q));
+        ++launches;
+        return FOLEY_OK;
+    };
+    const int RV = B2 * Lv;   // visual rows, flattened (no token conv on this stream, so samples need no halo)
     // ---- embed: audio0 = audio_embedder(x) + a_sync (fp32), v_cond0; LN+modulate for block 0
     {
         CombineArgs ca;
         ca.bias = audio_embed.b; ca.x = audio; ca.x_init = a_sync; ca.h = h_a; ca.eps = 1e-6f;
         ca.mod = tmod(0, 0); ca.shift_chunk = 0; ca.scale_chunk = 1; ca.rm = rm_a;
         ST_OK(proj_combine(st, x_in, L, B2, LAT, static_cast<long long>(L) * LAT, audio_embed, part_a, ca));
+        ST_OK(fork());
         CombineArgs cv;
         cv.x = vcond; cv.x_init = vcond0; cv.h = h_v; cv.eps = 1e-6f; cv.mod = tmod(0, 1); cv.rm = rm_v;
-        cv.C = C; cv.rows_total = B2 * Lv;
-        ST_OK(launch_combine(cv));
+        cv.C = C; cv.rows_total = RV;
+        ST_OK(combine_on(sv, cv));
     }
     const long long jb = static_cast<long long>(Sj) * C, jh = static_cast<long long>(Sj) * 128;
     for (int i = 0; i < NT; ++i) {
         const TripleW& w = triple[i];
         // -- joint self attention
         ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.qkv[0], 0, 3 * C, bf(qkv_a, C3, w.qkv[0].b, 0), 1, pick_bn(L, B2, 3 * C)));
-        ST_OK(gemm(st, h_v, Lv, B2, C, static_cast<long long>(Lv) * C, w.qkv[1], 0, 3 * C, bf(qkv_v, C3, w.qkv[1].b, 0), 1, 128));
+        ST_OK(gemm(sv, h_v, RV, 1, C, 0, w.qkv[1], 0, 3 * C, bf(qkv_v, C3, w.qkv[1].b, 0), 1, 64));
         for (int s = 0; s < 2; ++s) {
             QkvArgs q;
             q.src = s == 0 ? qkv_a : qkv_v; q.src_ld = 3 * C; q.n_parts = 3; q.H = H; q.L = s == 0 ? L : Lv;
@@ -659,10 +686,11 @@ foley_status Engine::step(cudaStream_t st) {
                 q.part[pz].dst = dsts[pz]; q.part[pz].dst_batch_stride = jb; q.part[pz].dst_head_stride = jh;
                 q.part[pz].seq_offset = s == 0 ? Lv : 0; q.part[pz].norm_w = norms[pz]; q.part[pz].src_col = pz * C;
             }
-            FOLEY_CUDA_OK(launch_k(qk_norm_rope_kernel, dim3(blocks_for(static_cast<long long>(q.rows_total) * 3 * H, 4)), dim3(128), 0, st, q));
-            ++launches;
+            ST_OK(qknorm_on(s == 0 ? st : sv, q));
         }
+        ST_OK(join());
         ST_OK(attn(Qj, Kj, Vj, Sj, Sj, jb, jh, false));
+        ST_OK(fork());
         {
             CombineArgs ca;
             ca.bias = w.self_proj[0].b; ca.gate = tmod(i, 0); ca.gate_chunk = 2; ca.x = audio; ca.h = h_a; ca.eps = 1e-6f;
@@ -671,24 +699,25 @@ foley_status Engine::step(cudaStream_t st) {
             CombineArgs cv = ca;
             cv.bias = w.self_proj[1].b; cv.gate = tmod(i, 1); cv.mod = tmod(i, 1); cv.x = vcond; cv.h = h_v; cv.rm = rm_v;
             cv.round_x = 1;
-            ST_OK(proj_combine(st, attn_out, Lv, B2, C, jb, w.self_proj[1], part_v, cv));
+            ST_OK(proj_combine(sv, attn_out, Lv, B2, C, jb, w.self_proj[1], part_v, cv));
         }
         // -- cross attention to text
         ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.cross_q[0], 0, C, bf(qkv_a, C, w.cross_q[0].b, 0), 1, 64));
-        ST_OK(gemm(st, h_v, Lv, B2, C, static_cast<long long>(Lv) * C, w.cross_q[1], 0, C, bf(qkv_v, C, w.cross_q[1].b, 0), 1, 64));
+        ST_OK(gemm(sv, h_v, RV, 1, C, 0, w.cross_q[1], 0, C, bf(qkv_v, C, w.cross_q[1].b, 0), 1, 64));
         for (int s = 0; s < 2; ++s) {
             QkvArgs q;
             q.src = s == 0 ? qkv_a : qkv_v; q.src_ld = C; q.n_parts = 1; q.H = H; q.L = s == 0 ? L : Lv;
             q.rows_total = B2 * q.L; q.norm_kind = 0; q.eps = 1e-6f; q.cos = rope_plain_cos; q.sin = rope_plain_sin;
             q.part[0].dst = Qj; q.part[0].dst_batch_stride = jb; q.part[0].dst_head_stride = jh;
             q.part[0].seq_offset = s == 0 ? Lv : 0; q.part[0].norm_w = w.cross_q_norm[s]; q.part[0].src_col = 0;
-            FOLEY_CUDA_OK(launch_k(qk_norm_rope_kernel, dim3(blocks_for(static_cast<long long>(q.rows_total) * H, 4)), dim3(128), 0, st, q));
-            ++launches;
+            ST_OK(qknorm_on(s == 0 ? st : sv, q));
         }
+        ST_OK(join());
         {
             const long long blk = static_cast<long long>(p.U) * T * C;
             ST_OK(attn(Qj, text_k + i * blk, text_v + i * blk, Sj, T, static_cast<long long>(T) * C,
                        static_cast<long long>(T) * 128, true));
+            ST_OK(fork());
             CombineArgs ca;
             ca.bias = w.cross_proj[0].b; ca.gate = tmod(i, 0); ca.gate_chunk = 5; ca.x = audio; ca.h = h_a; ca.eps = 1e-6f;
             ca.mod = tmod(i, 0); ca.shift_chunk = 6; ca.scale_chunk = 7; ca.rm = rm_a;
@@ -696,11 +725,11 @@ foley_status Engine::step(cudaStream_t st) {
             CombineArgs cv = ca;
             cv.bias = w.cross_proj[1].b; cv.gate = tmod(i, 1); cv.mod = tmod(i, 1); cv.x = vcond; cv.h = h_v; cv.rm = rm_v;
             cv.round_x = 1;
-            ST_OK(proj_combine(st, attn_out, Lv, B2, C, jb, w.cross_proj[1], part_v, cv));
+            ST_OK(proj_combine(sv, attn_out, Lv, B2, C, jb, w.cross_proj[1], part_v, cv));
         }
         // -- MLPs
         ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.fc1[0], 0, F, bf(mlp_a, F, w.fc1[0].b, ACT_GELU_TANH), 1, pick_bn(L, B2, F)));
-        ST_OK(gemm(st, h_v, Lv, B2, C, static_cast<long long>(Lv) * C, w.fc1[1], 0, F, bf(mlp_v, F, w.fc1[1].b, ACT_GELU_TANH), 1, 128));
+        ST_OK(gemm(sv, h_v, RV, 1, C, 0, w.fc1[1], 0, F, bf(mlp_v, F, w.fc1[1].b, ACT_GELU_TANH), 1, 64));
         {
             const bool last = i == NT - 1;
             CombineArgs ca;
@@ -712,9 +741,10 @@ foley_status Engine::step(cudaStream_t st) {
             CombineArgs cv;
             cv.bias = w.fc2[1].b; cv.gate = tmod(i, 1); cv.gate_chunk = 8; cv.x = vcond; cv.rm = rm_v; cv.round_x = 1;
             if (!last) { cv.h = h_v; cv.eps = 1e-6f; cv.mod = tmod(i + 1, 1); cv.shift_chunk = 0; cv.scale_chunk = 1; }
-            ST_OK(proj_combine(st, mlp_v, Lv, B2, F, static_cast<long long>(Lv) * F, w.fc2[1], part_v, cv));
+            ST_OK(proj_combine(sv, mlp_v, RV, 1, F, 0, w.fc2[1], part_v, cv));
         }
     }
+    ST_OK(join());   // the side branch must be complete before the step (graph) ends
     // ---- single-stream blocks (hifi_foley.py:364-390)
     const long long sb = static_cast<long long>(L) * C, sh = static_cast<long long>(L) * 128;
     for (int j = 0; j < NS; ++j) {

@@ -93,6 +93,8 @@ class Engine {
     int64_t graph_launches_per_step = 0;
     int cur_G = 1;
     int num_sms = 148;
+    cudaStream_t side_stream = nullptr;  // visual-stream branch of the step
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t own_stream = nullptr;   // blocking stream used when the caller passes NULL (legacy stream cannot be captured)
     // scratch of set_conditions / prepare_timesteps (plan-owned)
     bf16 *sc_clip = nullptr, *sc_sync = nullptr, *sc_text = nullptr, *sc_s0 = nullptr, *sc_s1 = nullptr, *sc_s2 = nullptr;
