@@ -7,7 +7,7 @@
 // batch its own zero halo for the k=3 / k=7 convolutions and the transposed-conv polyphase form.
 // W is a K-major weight matrix [N, taps*K].  One CTA computes one 128 x BN output tile (optionally one
 // K-split of it): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma
-// issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> fused epilogue -> global).
+// issuer, warps 2..9 = epilogue (tcgen05.ld -> registers -> fused epilogue -> global).
 //
 // Replaces, on the reference path: F.linear / Conv1d(k=1,3) in hifi_foley.py:216-331,364-390,
 // mlp_layers.py:104-149, and the DAC decoder convs in dac.py:28-44,98-149.
@@ -65,8 +65,8 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int THREADS = 192;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 3 * 256 * 4 /*epilogue params*/;
+    static constexpr int THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -79,7 +79,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 }
 
 template <int BN, bool kTF32>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const GemmArgs g) {
     using Cfg = GemmCfg<BN, kTF32>;
@@ -93,6 +93,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     uint64_t* empty_bar = bars + Cfg::STAGES;
     uint64_t* tmem_full_bar = bars + 2 * Cfg::STAGES;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+    float* epi_f = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);   // [3][256]: bias, alpha, 1/alpha
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -207,36 +208,57 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             else umma_commit(tmem_full_bar);  // accumulator complete
         }
     } else {
-        // ------------------------------------------------------------- epilogue warps (2..5)
+        // ------------------------------------------------------------- epilogue warps (2..9)
+        // Two warps per TMEM lane quarter; each takes every other 32-column chunk.  Per-column parameters (bias,
+        // snake alpha and 1/alpha) are staged in shared memory while the mainloop runs.
         const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;    // which interleaved set of column chunks
         const int r = m0 + q * 32 + lane;    // output row within the sample
+        const GemmEpi& e = g.epi;
+        {
+            const int et = threadIdx.x - 64;
+            for (int c = et; c < BN; c += 256) {
+                const int col = n0 + c;
+                float bv = 0.f, al = 0.f, ial = 0.f;
+                if (col < g.n) {
+                    if (e.mode == EPI_DAC) {
+                        const int ch = e.ch_mod ? col % e.ch_mod : col;
+                        if (e.bias) bv = reinterpret_cast<const float*>(e.bias)[ch];
+                        if (e.alpha) { al = e.alpha[ch]; ial = 1.0f / (al + 1e-9f); }
+                    } else if (e.bias) {
+                        bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.bias)[col]);
+                    }
+                }
+                epi_f[c] = bv; epi_f[256 + c] = al; epi_f[512 + c] = ial;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         pdl_wait();                          // outputs may alias buffers the predecessor still reads
         const bool acc_ok = mbar_wait(tmem_full_bar, 0, 0x300);
         pdl_trigger();                       // mainloop done: the next kernel may start its prologue
         tc_fence_after();
-        const GemmEpi& e = g.epi;
         const bool row_ok = r < g.rows;
         const long long row_off = static_cast<long long>(batch) * e.out_batch_stride +
                                   static_cast<long long>(r) * e.ldo;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN && acc_ok && g.dbg_stop == 0; c0 += 32) {
+        for (int c0 = half * 32; c0 < BN && acc_ok && g.dbg_stop == 0; c0 += 64) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
             tmem_ld_wait();
             const int col = n0 + c0;
             if (!row_ok || col >= g.n || num_kb <= 0) continue;
+            const float* pb = epi_f + c0;
             if (e.mode == EPI_BF16) {
-                const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(e.bias);
                 __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out) + row_off + col;
                 uint32_t packed[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
-                    if (bias) {
-                        a0 += __bfloat162float(bias[col + j]);
-                        a1 += __bfloat162float(bias[col + j + 1]);
-                    }
-                    if (e.act != ACT_NONE) {
+                    float a0 = __uint_as_float(v[j]) + pb[j], a1 = __uint_as_float(v[j + 1]) + pb[j + 1];
+                    if (e.act == ACT_SILU) {
+                        a0 = bf16_round(a0); a1 = bf16_round(a1);
+                        a0 = __fdividef(a0, 1.0f + __expf(-a0));
+                        a1 = __fdividef(a1, 1.0f + __expf(-a1));
+                    } else if (e.act != ACT_NONE) {
                         a0 = apply_act(bf16_round(a0), e.act);
                         a1 = apply_act(bf16_round(a1), e.act);
                     }
@@ -251,10 +273,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 uint32_t packed[8];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    float g0 = bf16_round(__uint_as_float(v[j])), u0 = bf16_round(__uint_as_float(v[j + 1]));
-                    float g1 = bf16_round(__uint_as_float(v[j + 2])), u1 = bf16_round(__uint_as_float(v[j + 3]));
-                    float s0 = bf16_round(g0 / (1.0f + expf(-g0))) * u0;
-                    float s1 = bf16_round(g1 / (1.0f + expf(-g1))) * u1;
+                    const float g0 = bf16_round(__uint_as_float(v[j])), u0 = bf16_round(__uint_as_float(v[j + 1]));
+                    const float g1 = bf16_round(__uint_as_float(v[j + 2])), u1 = bf16_round(__uint_as_float(v[j + 3]));
+                    const float s0 = bf16_round(__fdividef(g0, 1.0f + __expf(-g0))) * u0;
+                    const float s1 = bf16_round(__fdividef(g1, 1.0f + __expf(-g1))) * u1;
                     packed[j >> 2] = pack_bf16x2(s0, s1);
                 }
                 uint4* dst = reinterpret_cast<uint4*>(out);
@@ -269,7 +291,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
             } else {  // EPI_DAC
-                const float* bias = reinterpret_cast<const float*>(e.bias);
                 const long long flat0 = static_cast<long long>(r) * e.ldo + col;
                 const bool windowed = e.flat_hi > e.flat_lo;
                 float* out = e.out ? reinterpret_cast<float*>(e.out) + row_off + col : nullptr;
@@ -278,24 +299,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 const bool full_ok = !windowed || (flat0 >= e.flat_lo && flat0 + 32 <= e.flat_hi);
                 const bool any_ok = !windowed || (flat0 + 32 > e.flat_lo && flat0 < e.flat_hi);
                 if (!any_ok) continue;
-                float y[32], z[32];
+                const bool snake = e.alpha != nullptr && e.act != ACT_TANH;
+                float y[32];
+                if (res && full_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int ch = e.ch_mod ? (col + j) % e.ch_mod : (col + j);
-                    float a = __uint_as_float(v[j]);
-                    if (bias) a += bias[ch];
-                    if (res && (full_ok || (flat0 + j >= e.flat_lo && flat0 + j < e.flat_hi))) a += res[j];
-                    y[j] = a;
-                    if (e.act == ACT_TANH) {
-                        z[j] = tanhf(a);
-                    } else if (e.alpha) {
-                        const float al = e.alpha[ch];
-                        const float sn = sinf(al * a);
-                        z[j] = a + (1.0f / (al + 1e-9f)) * sn * sn;
-                    } else {
-                        z[j] = a;
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 rv = reinterpret_cast<const float4*>(res)[j];
+                        y[4 * j] = rv.x; y[4 * j + 1] = rv.y; y[4 * j + 2] = rv.z; y[4 * j + 3] = rv.w;
                     }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        y[j] = (res && flat0 + j >= e.flat_lo && flat0 + j < e.flat_hi) ? res[j] : 0.f;
                 }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(v[j]) + pb[j];
                 if (full_ok) {
                     if (out) {
 #pragma unroll
@@ -304,15 +322,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     }
                     if (out2) {
 #pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (e.act == ACT_TANH) y[j] = tanhf(y[j]);
+                            else if (snake) { const float sn = __sinf(pb[256 + j] * y[j]); y[j] = fmaf(pb[512 + j] * sn, sn, y[j]); }
+                        }
+#pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            reinterpret_cast<float4*>(out2)[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
+                            reinterpret_cast<float4*>(out2)[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         if (flat0 + j >= e.flat_lo && flat0 + j < e.flat_hi) {
                             if (out) out[j] = y[j];
-                            if (out2) out2[j] = z[j];
+                            if (out2) {
+                                float z = y[j];
+                                if (e.act == ACT_TANH) z = tanhf(z);
+                                else if (snake) { const float sn = __sinf(pb[256 + j] * z); z = fmaf(pb[512 + j] * sn, sn, z); }
+                                out2[j] = z;
+                            }
                         }
                     }
                 }

@@ -31,6 +31,20 @@ inline PFN_encodeTiled get_encode_tiled() {
 
 enum DType : int { DT_BF16 = 0, DT_F32 = 1 };
 
+inline CUtensorMapL2promotion tma_l2_promotion() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FOLEY_TMA_L2PROMO");
+        v = e ? atoi(e) : 3;
+    }
+    switch (v) {
+        case 0: return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+        case 1: return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+        case 2: return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+        default: return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }
+}
+
 // A K-major operand view: element (b, r, k) lives at ptr + b*batch_stride + r*ld + k (elements).
 struct Operand {
     const void* ptr = nullptr;
@@ -60,7 +74,7 @@ inline bool encode_operand_map(CUtensorMap* out, const Operand& t, int box_rows,
     }
     CUresult r = enc(out, t.dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
                      3, const_cast<void*>(t.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_SWIZZLE_128B, tma_l2_promotion(),
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         if (err) {

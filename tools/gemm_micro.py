@@ -20,6 +20,7 @@ ap.add_argument("--splits", type=int, default=0)
 ap.add_argument("--iters", type=int, default=50)
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--all", action="store_true")
+ap.add_argument("--dbg", type=int, default=0, help="partial pipeline: 2 = TMA only, 3 = TMA+MMA (no epilogue)")
 a = ap.parse_args()
 lib = ctypes.CDLL(os.path.join(ROOT, "comfyui-hunyuanvideo-foley_b200", "libfoley_b200.so"))
 lib.foley_last_error.restype = ctypes.c_char_p
@@ -48,7 +49,7 @@ def run(name, bn):
     ldo = out.shape[-1]
 
     def launch():
-        s = lib.foley_gemm(x.data_ptr(), 0, B2, L, K, K, L * K, w.data_ptr(), N, taps, -(taps // 2), 1, sp, bn, mode, 0,
+        s = lib.foley_gemm(x.data_ptr(), 0, B2, L, K, K, L * K, w.data_ptr(), N, taps, -(taps // 2), 1, sp, bn | (a.dbg << 16), mode, 0,
                            None, out.data_ptr(), ldo, L * ldo, B2 * L * ldo, None)
         assert s == 0, lib.foley_last_error()
 
