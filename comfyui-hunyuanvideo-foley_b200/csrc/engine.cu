@@ -364,22 +364,42 @@ foley_status Engine::alloc_plan(int B, int U, int L, int Lv, int S, int T) {
     return FOLEY_OK;
 }
 
-// Tile width: 256-wide tiles halve the A-operand re-reads and the per-SM TMA ingress per MMA cycle (858 vs 526
-// TFLOP/s on the ConvMLP GEMM, profiles/r01_gemm_micro.txt); use them when N is wide enough that the grid still
-// covers most SMs, else 128.
-int Engine::pick_bn(int rows, int batch, int n) const {
+// Tile-shape / K-split planner.  The kernel is bound by the TMA round trip per k-block (profiles/r01_gemm_micro.txt:
+// ~0.30 us per k-block with 128-wide tiles, ~0.38 us with 256-wide ones, ~5 us of launch + prologue + epilogue per
+// CTA wave), so the cost model is  waves x (k-blocks per CTA x t_kb + t_fixed)  and the planner picks the
+// (tile width, split) pair that minimises it.
+void Engine::plan_gemm(int rows, int batch, int n, int kblocks, bool can_split, int* bn_out, int* splits_out) const {
     const long long m_tiles = static_cast<long long>((rows + 127) / 128) * batch;
-    if (n % 256 == 0 && m_tiles * (n / 256) >= (num_sms * 11) / 20) return 256;
-    return 128;
+    double best = 1e30;
+    int best_bn = 128, best_s = 1;
+    const int smax = can_split ? std::min(max_splits, max_splits_used) : 1;
+    for (int bn : {128, 256}) {
+        const long long n_tiles = (n + bn - 1) / bn;
+        const double t_kb = bn == 128 ? 0.30 : 0.38;
+        for (int s = 1; s <= smax; ++s) {
+            if (s > 1 && kblocks / s < 4) break;
+            const long long ctas = m_tiles * n_tiles * s;
+            const long long waves = (ctas + num_sms - 1) / num_sms;
+            const int kb_per = (kblocks + s - 1) / s;
+            const double t = waves * (kb_per * t_kb + 5.0) + (s - 1) * 0.4;   // extra partials cost a little downstream
+            if (t < best - 1e-9) { best = t; best_bn = bn; best_s = s; }
+        }
+    }
+    *bn_out = best_bn;
+    *splits_out = best_s;
+}
+
+int Engine::pick_bn(int rows, int batch, int n, int kblocks) const {
+    int bn, s;
+    plan_gemm(rows, batch, n, kblocks, false, &bn, &s);
+    return bn;
 }
 
 int Engine::pick_splits(int rows, int batch, int n, int kblocks, int bn) const {
-    const long long tiles = static_cast<long long>((n + bn - 1) / bn) * ((rows + 127) / 128) * batch;
-    if (tiles * 10 >= static_cast<long long>(num_sms) * 7) return 1;
-    long long s = num_sms / std::max<long long>(tiles, 1);
-    s = std::min<long long>(s, std::min(max_splits, max_splits_used));
-    s = std::min<long long>(s, std::max(1, kblocks / 4));
-    return static_cast<int>(std::max<long long>(s, 1));
+    (void)bn;
+    int b2, s;
+    plan_gemm(rows, batch, n, kblocks, true, &b2, &s);
+    return s;
 }
 
 foley_status Engine::gemm(cudaStream_t st, const bf16* A, int rows, int batch, long long lda, long long a_bs,
@@ -406,9 +426,9 @@ foley_status Engine::gemm(cudaStream_t st, const bf16* A, int rows, int batch, l
 // GEMM with fp32 K-split partials followed by the fused reduce + bias + gate + residual + LayerNorm/modulate.
 foley_status Engine::proj_combine(cudaStream_t st, const bf16* A, int rows, int batch, long long lda, long long a_bs,
                                   const LinearW& W, float* partials, CombineArgs ca) {
-    const int bn = 128;
     const int kblocks = W.k * W.taps / 64;
-    const int splits = pick_splits(rows, batch, W.n, kblocks, bn);
+    int bn = 128, splits = 1;
+    plan_gemm(rows, batch, W.n, kblocks, true, &bn, &splits);
     GemmEpi e;
     e.mode = EPI_F32;
     e.out = partials;
@@ -673,7 +693,7 @@ foley_status Engine::step(cudaStream_t st) {
     for (int i = 0; i < NT; ++i) {
         const TripleW& w = triple[i];
         // -- joint self attention
-        ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.qkv[0], 0, 3 * C, bf(qkv_a, C3, w.qkv[0].b, 0), 1, pick_bn(L, B2, 3 * C)));
+        ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.qkv[0], 0, 3 * C, bf(qkv_a, C3, w.qkv[0].b, 0), 1, pick_bn(L, B2, 3 * C, C / 64)));
         ST_OK(gemm(sv, h_v, RV, 1, C, 0, w.qkv[1], 0, 3 * C, bf(qkv_v, C3, w.qkv[1].b, 0), 1, 64));
         for (int s = 0; s < 2; ++s) {
             QkvArgs q;
@@ -728,7 +748,7 @@ foley_status Engine::step(cudaStream_t st) {
             ST_OK(proj_combine(sv, attn_out, Lv, B2, C, jb, w.cross_proj[1], part_v, cv));
         }
         // -- MLPs
-        ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.fc1[0], 0, F, bf(mlp_a, F, w.fc1[0].b, ACT_GELU_TANH), 1, pick_bn(L, B2, F)));
+        ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.fc1[0], 0, F, bf(mlp_a, F, w.fc1[0].b, ACT_GELU_TANH), 1, pick_bn(L, B2, F, C / 64)));
         ST_OK(gemm(sv, h_v, RV, 1, C, 0, w.fc1[1], 0, F, bf(mlp_v, F, w.fc1[1].b, ACT_GELU_TANH), 1, 64));
         {
             const bool last = i == NT - 1;
@@ -749,7 +769,7 @@ foley_status Engine::step(cudaStream_t st) {
     const long long sb = static_cast<long long>(L) * C, sh = static_cast<long long>(L) * 128;
     for (int j = 0; j < NS; ++j) {
         const SingleW& w = single[j];
-        ST_OK(gemm(st, h_a, L, B2, C, sb, w.qkv, 0, 3 * C, bf(qkv_a, C3, w.qkv.b, 0), 1, pick_bn(L, B2, 3 * C)));
+        ST_OK(gemm(st, h_a, L, B2, C, sb, w.qkv, 0, 3 * C, bf(qkv_a, C3, w.qkv.b, 0), 1, pick_bn(L, B2, 3 * C, C / 64)));
         {
             QkvArgs q;
             q.src = qkv_a; q.src_ld = 3 * C; q.n_parts = 3; q.H = H; q.L = L; q.rows_total = B2 * L;
@@ -770,7 +790,7 @@ foley_status Engine::step(cudaStream_t st) {
             ca.mod = smod(j); ca.shift_chunk = 3; ca.scale_chunk = 4; ca.rm = rm_a;
             ST_OK(proj_combine(st, attn_out, L, B2, C, sb, w.linear1, part_a, ca));
         }
-        ST_OK(gemm(st, h_a, L, B2, C, sb, w.w13, 0, 2 * Hs, bf(mlp_a, Hs, nullptr, 0, EPI_SWIGLU), 1, pick_bn(L, B2, 2 * Hs)));
+        ST_OK(gemm(st, h_a, L, B2, C, sb, w.w13, 0, 2 * Hs, bf(mlp_a, Hs, nullptr, 0, EPI_SWIGLU), 1, pick_bn(L, B2, 2 * Hs, 3 * C / 64)));
         {
             const bool last = j == NS - 1;
             CombineArgs ca;

@@ -136,7 +136,8 @@ class Engine {
     void free_plan();
     template <typename T> foley_status palloc(T** p, size_t count);
     int pick_splits(int rows, int batch, int n, int kblocks, int bn) const;
-    int pick_bn(int rows, int batch, int n) const;
+    int pick_bn(int rows, int batch, int n, int kblocks) const;
+    void plan_gemm(int rows, int batch, int n, int kblocks, bool can_split, int* bn_out, int* splits_out) const;
     foley_status proj_combine(cudaStream_t st, const bf16* A, int rows, int batch, long long lda, long long a_bs,
                               const LinearW& W, float* partials, CombineArgs ca);
 };

@@ -54,14 +54,18 @@ struct GemmArgs {
     GemmEpi epi;
 };
 
-template <int BN, bool kTF32>
+// kPair: the CTA pair of a (2,1,1) cluster computes a 256 x BN tile with tcgen05.mma.cta_group::2 — each CTA holds
+// its own 128 rows of A and only HALF of the B tile, so the per-SM TMA ingress per MMA cycle (what bounds this
+// kernel) drops by a third and the same shared memory holds twice the MMA time.
+template <int BN, bool kTF32, bool kPair = false>
 struct GemmCfg {
     static constexpr int BM = 128;
     static constexpr int BK_BYTES = 128;                      // one swizzle-128B row
     static constexpr int BK = kTF32 ? 32 : 64;                // elements per k-block
     static constexpr int UMMA_K = kTF32 ? 8 : 16;             // 32 bytes per instruction
     static constexpr int A_BYTES = BM * BK_BYTES;             // 16 KB
-    static constexpr int B_BYTES = BN * BK_BYTES;
+    static constexpr int B_ROWS = kPair ? BN / 2 : BN;        // rows of B this CTA loads
+    static constexpr int B_BYTES = B_ROWS * BK_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
@@ -78,11 +82,11 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     }
 }
 
-template <int BN, bool kTF32>
+template <int BN, bool kTF32, bool kPair = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const GemmArgs g) {
-    using Cfg = GemmCfg<BN, kTF32>;
+    using Cfg = GemmCfg<BN, kTF32, kPair>;
     extern __shared__ uint8_t smem_raw[];
     // swizzle-128B tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -92,8 +96,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + Cfg::STAGES;
     uint64_t* tmem_full_bar = bars + 2 * Cfg::STAGES;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
-    float* epi_f = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);   // [3][256]: bias, alpha, 1/alpha
+    uint64_t* peer_ready = bars + 2 * Cfg::STAGES + 1;   // pair mode, leader only: the peer CTA's stage has landed
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * Cfg::STAGES + 1);
+    float* epi_f = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);   // barriers use <= 26*8 bytes   // [3][256]: bias, alpha, 1/alpha
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -108,33 +113,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const int kb_end = static_cast<int>((static_cast<long long>(kb_total) * (split + 1)) / g.splits);
     const int num_kb = kb_end - kb_begin;
 
-    // Thread-block cluster (cx along the m-tile axis, cy along the n-tile axis; 1x1 when launched without one):
-    // CTAs of a cluster column share the A tile, CTAs of a cluster row share the B tile.  Each CTA loads a 1/cy
-    // slice of A and a 1/cx slice of B and multicasts it, so a tile crosses the L2 -> GPC fabric once per cluster
-    // instead of once per CTA (the un-clustered kernel saturates at ~5.3 KB/cycle of chip-wide SM ingress).
-    const uint32_t cx = cluster_nctaid_x(), cy = cluster_nctaid_y();
-    const uint32_t rx = cluster_ctaid_x(), ry = cluster_ctaid_y();
-    const bool clustered = cx * cy > 1;
-    uint32_t a_mask = 0, b_mask = 0;
-    for (uint32_t j = 0; j < cy; ++j) a_mask |= 1u << (rx + j * cx);
-    for (uint32_t i = 0; i < cx; ++i) b_mask |= 1u << (i + ry * cx);
-    const int a_rows = Cfg::BM / static_cast<int>(cy), b_rows = BN / static_cast<int>(cx);
+    // CTA pair: rank 0 (even m-tile) is the leader — it owns the full barriers and issues the MMAs for both.
+    const uint32_t pair_rank = kPair ? cluster_ctarank() : 0;
+    const bool leader = pair_rank == 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
         tma_prefetch_desc(&tm_b);
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], cx + cy - 1);   // one release per CTA that multicasts into this CTA's stage
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&peer_ready[s], 1);
         }
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     } else if (warp == 1) {
-        tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+        if constexpr (kPair) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr_smem);
+        else tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
     }
     tc_fence_before();
     __syncthreads();
-    if (clustered) cluster_sync_all();   // peers' barriers must be initialised before anything is multicast
+    if constexpr (kPair) cluster_sync_all();   // the peer's barriers must exist before anything is signalled to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -143,15 +142,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     } else if (warp == 0) {
         // ------------------------------------------------------------- TMA producer
         if (lane == 0) {
+            // Each CTA's loads complete on its OWN full barrier; in pair mode the peer forwards "stage landed" to the
+            // leader with one remote arrive per stage (remote complete_tx from TMA, the cta_group::2 TMA form, measured
+            // 2.4x slower here).
             auto load_b = [&](int i) {
                 const int s = i % Cfg::STAGES;
                 const int kb = kb_begin + i;
                 mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                if (cx > 1)
-                    tma_load_3d_mc(smem_b + s * Cfg::B_BYTES + rx * b_rows * Cfg::BK_BYTES, &tm_b, &full_bar[s],
-                                   kb * Cfg::BK, n0 + rx * b_rows, 0, static_cast<uint16_t>(b_mask));
-                else
-                    tma_load_3d(smem_b + s * Cfg::B_BYTES, &tm_b, &full_bar[s], kb * Cfg::BK, n0, 0);  // rank-3 map
+                tma_load_3d(smem_b + s * Cfg::B_BYTES, &tm_b, &full_bar[s], kb * Cfg::BK,
+                            n0 + static_cast<int>(pair_rank) * Cfg::B_ROWS, 0);   // rank-3 map; pair: this CTA's half
             };
             auto load_a = [&](int i) {
                 const int s = i % Cfg::STAGES;
@@ -159,11 +158,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 const int tap = kb / g.kb_per_tap;
                 const int kcol = (kb - tap * g.kb_per_tap) * Cfg::BK;
                 const int arow = m0 + g.tap_off0 + tap * g.tap_stride;
-                if (cy > 1)
-                    tma_load_3d_mc(smem_a + s * Cfg::A_BYTES + ry * a_rows * Cfg::BK_BYTES, &tm_a, &full_bar[s], kcol,
-                                   arow + ry * a_rows, batch, static_cast<uint16_t>(a_mask));
-                else
-                    tma_load_3d(smem_a + s * Cfg::A_BYTES, &tm_a, &full_bar[s], kcol, arow, batch);
+                tma_load_3d(smem_a + s * Cfg::A_BYTES, &tm_a, &full_bar[s], kcol, arow, batch);
             };
             // Weights do not depend on the previous kernel: fill the ring with B tiles before waiting on it
             // (programmatic dependent launch), so the weight stream's HBM latency hides under the predecessor.
@@ -181,31 +176,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------- MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, Cfg::BM, BN);
+        // ------------------------------------------------------------- MMA issuer (one thread; pair: leader CTA only)
+        if (lane == 0 && !leader) {
+            // peer CTA of a pair: forward each landed stage to the leader
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % Cfg::STAGES;
+                const uint32_t ph = (i / Cfg::STAGES) & 1;
+                if (!mbar_wait(&full_bar[s], ph, 0x400 + i)) break;
+                mbar_arrive_cluster(mapa_u32(smem_u32(&peer_ready[s]), 0));
+            }
+        }
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, kPair ? 2 * Cfg::BM : Cfg::BM, BN);
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % Cfg::STAGES;
                 const uint32_t ph = (i / Cfg::STAGES) & 1;
                 if (!mbar_wait(&full_bar[s], ph, 0x200 + i)) break;
+                if constexpr (kPair) { if (!mbar_wait(&peer_ready[s], ph, 0x500 + i)) break; }
                 tc_fence_after();
-                if (g.dbg_stop == 2) { mbar_arrive(&empty_bar[s]); continue; }
+                if (g.dbg_stop == 2) {
+                    if constexpr (kPair) { mbar_arrive(&empty_bar[s]); mbar_arrive_cluster(mapa_u32(smem_u32(&empty_bar[s]), 1)); }
+                    else mbar_arrive(&empty_bar[s]);
+                    continue;
+                }
                 const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + s * Cfg::A_BYTES));
                 const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::B_BYTES));
 #pragma unroll
                 for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; ++k) {
                     // advance 32 bytes (= 2 x 16 B units) along K inside the swizzle atom
-                    if constexpr (kTF32)
-                        umma_tf32(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0);
-                    else
-                        umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0);
+                    const uint32_t acc = (i | k) != 0;
+                    if constexpr (kPair) {
+                        if constexpr (kTF32) umma_tf32_pair(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+                        else umma_bf16_pair(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+                    } else {
+                        if constexpr (kTF32) umma_tf32(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+                        else umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+                    }
                 }
-                // free the stage once these MMAs retire — in every CTA that writes into it
-                if (clustered) umma_commit_mc(&empty_bar[s], static_cast<uint16_t>(a_mask | b_mask));
+                // free the stage (in both CTAs of a pair) once these MMAs retire
+                if constexpr (kPair) umma_commit_pair(&empty_bar[s]);
                 else umma_commit(&empty_bar[s]);
             }
-            if (g.dbg_stop == 2) mbar_arrive(tmem_full_bar);
-            else umma_commit(tmem_full_bar);  // accumulator complete
+            if (g.dbg_stop == 2) {
+                mbar_arrive(tmem_full_bar);
+                if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_full_bar), 1));
+            } else {
+                if constexpr (kPair) umma_commit_pair(tmem_full_bar);   // accumulators complete in both CTAs
+                else umma_commit(tmem_full_bar);
+            }
         }
     } else {
         // ------------------------------------------------------------- epilogue warps (2..9)
@@ -350,11 +368,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (kPair) cluster_sync_all();   // the peer may still read this CTA's B half / signal its barriers
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        if constexpr (kPair) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+        else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
-    if (clustered) cluster_sync_all();   // no CTA may exit while peers can still signal its barriers
 }
 
 }  // namespace foley

@@ -124,22 +124,14 @@ inline int default_prefetch_distance() {
     return v;
 }
 
-// Default cluster policy (override: FOLEY_GEMM_CLUSTER="XxY"): 2 along m when the m-tile count is even, 2 along n
-// when there are at least two n-tiles.
-inline void cluster_shape_for(long long m_tiles, long long n_tiles, int want_x, int want_y, int* cx, int* cy) {
-    static int env_x = -1, env_y = -1;
-    if (env_x < 0) {
-        env_x = 1; env_y = 1;
-        if (const char* e = getenv("FOLEY_GEMM_CLUSTER")) {
-            int a = 0, b = 0;
-            if (sscanf(e, "%dx%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= 8) { env_x = a; env_y = b; }
-        }
+// CTA-pair tiles on by default (FOLEY_GEMM_PAIR=0 disables).
+inline int default_pair_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FOLEY_GEMM_PAIR");
+        v = e ? atoi(e) : 0;   // measured 10-15 % slower than single-CTA tiles at every shape of this model
     }
-    int x = want_x > 0 ? want_x : env_x, y = want_y > 0 ? want_y : env_y;
-    while (x > 1 && m_tiles % x != 0) x /= 2;
-    while (y > 1 && n_tiles < y) y /= 2;
-    if ((x & (x - 1)) || (y & (y - 1))) { x = 1; y = 1; }   // slices must divide the tile evenly
-    *cx = x; *cy = y;
+    return v;
 }
 
 struct GemmLaunch {
@@ -151,16 +143,17 @@ struct GemmLaunch {
     int bn = 128;              // tile width: 64, 128 or 256
     int dbg_stop = 0;
     int prefetch_b = -1;       // -1: default distance
-    int cluster_x = 0, cluster_y = 0;  // 0: default policy
+    int pair = -1;             // CTA-pair (cta_group::2) tiles: -1 default policy, 0 off, 1 on when the shape allows
     long long out_rows = 0;    // output rows per sample (0 -> a.rows); may exceed a.rows (halo rows read as zero)
     GemmEpi epi;
 };
 
-template <int BN, bool kTF32>
+template <int BN, bool kTF32, bool kPair = false>
 inline cudaError_t launch_gemm_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& args,
-                                    dim3 grid, cudaStream_t stream, int cx = 1, int cy = 1) {
-    using Cfg = GemmCfg<BN, kTF32>;
-    auto kern = gemm_tcgen05_kernel<BN, kTF32>;
+                                    dim3 grid, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, kTF32, kPair>;
+    auto kern = gemm_tcgen05_kernel<BN, kTF32, kPair>;
+    const int cx = kPair ? 2 : 1, cy = 1;
     static bool attr_set = false;
     if (!attr_set) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -205,6 +198,9 @@ inline bool gemm_init_attributes(std::string* err) {
     set(gemm_tcgen05_kernel<64, false>, GemmCfg<64, false>::SMEM_BYTES);
     set(gemm_tcgen05_kernel<128, false>, GemmCfg<128, false>::SMEM_BYTES);
     set(gemm_tcgen05_kernel<256, false>, GemmCfg<256, false>::SMEM_BYTES);
+    set(gemm_tcgen05_kernel<128, false, true>, GemmCfg<128, false, true>::SMEM_BYTES);
+    set(gemm_tcgen05_kernel<256, false, true>, GemmCfg<256, false, true>::SMEM_BYTES);
+    set(gemm_tcgen05_kernel<256, true, true>, GemmCfg<256, true, true>::SMEM_BYTES);
     set(gemm_tcgen05_kernel<64, true>, GemmCfg<64, true>::SMEM_BYTES);
     set(gemm_tcgen05_kernel<128, true>, GemmCfg<128, true>::SMEM_BYTES);
     set(gemm_tcgen05_kernel<256, true>, GemmCfg<256, true>::SMEM_BYTES);
@@ -220,18 +216,19 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
     const int bk = tf32 ? 32 : 64;
     if (L.a.k % bk != 0) { if (err) *err = "GEMM K must be a multiple of the 128-byte k-block"; return false; }
     if (L.n % 16 != 0) { if (err) *err = "GEMM N must be a multiple of 16"; return false; }
-    // cluster shape: pairs of m-tiles share B, pairs of n-tiles share A (see gemm.cuh)
     const long long out_rows_c = L.out_rows > 0 ? L.out_rows : L.a.rows;
     const long long mt = ((out_rows_c + 127) / 128) * (L.a.batch > 0 ? L.a.batch : 1);
     const long long nt = (L.n + L.bn - 1) / L.bn;
-    int cx = 1, cy = 1;
-    cluster_shape_for(mt, nt, L.cluster_x, L.cluster_y, &cx, &cy);
+    // CTA-pair (cta_group::2) tiles: need an even number of m-tiles and a 128/256-wide tile
+    int pair = L.pair >= 0 ? L.pair : default_pair_mode();
+    if (mt % 2 != 0 || (L.bn != 256 && L.bn != 128) || (tf32 && L.bn != 256)) pair = 0;
+    const int cx = 1, cy = 1;
     CUtensorMap ma, mb;
     if (!encode_operand_map(&ma, L.a, 128 / cy, err)) return false;
     Operand wb;
     wb.ptr = L.w; wb.dtype = L.a.dtype; wb.k = L.a.k * L.taps; wb.rows = L.n; wb.batch = 1;
     wb.ld = wb.k; wb.batch_stride = wb.k * wb.rows;
-    if (!encode_operand_map(&mb, wb, L.bn / cx, err)) return false;
+    if (!encode_operand_map(&mb, wb, pair ? L.bn / 2 : L.bn, err)) return false;
 
     GemmArgs args;
     const long long out_rows = L.out_rows > 0 ? L.out_rows : L.a.rows;
@@ -251,14 +248,17 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
               static_cast<unsigned>(((nt + cy - 1) / cy) * cy), static_cast<unsigned>(args.splits));
     cudaError_t e = cudaSuccess;
     if (!tf32) {
-        if (L.bn == 64) e = launch_gemm_inst<64, false>(ma, mb, args, grid, stream, cx, cy);
-        else if (L.bn == 128) e = launch_gemm_inst<128, false>(ma, mb, args, grid, stream, cx, cy);
-        else if (L.bn == 256) e = launch_gemm_inst<256, false>(ma, mb, args, grid, stream, cx, cy);
+        if (L.bn == 64) e = launch_gemm_inst<64, false>(ma, mb, args, grid, stream);
+        else if (L.bn == 128) e = pair ? launch_gemm_inst<128, false, true>(ma, mb, args, grid, stream)
+                                       : launch_gemm_inst<128, false>(ma, mb, args, grid, stream);
+        else if (L.bn == 256) e = pair ? launch_gemm_inst<256, false, true>(ma, mb, args, grid, stream)
+                                       : launch_gemm_inst<256, false>(ma, mb, args, grid, stream);
         else { if (err) *err = "unsupported BN"; return false; }
     } else {
-        if (L.bn == 64) e = launch_gemm_inst<64, true>(ma, mb, args, grid, stream, cx, cy);
-        else if (L.bn == 128) e = launch_gemm_inst<128, true>(ma, mb, args, grid, stream, cx, cy);
-        else if (L.bn == 256) e = launch_gemm_inst<256, true>(ma, mb, args, grid, stream, cx, cy);
+        if (L.bn == 64) e = launch_gemm_inst<64, true>(ma, mb, args, grid, stream);
+        else if (L.bn == 128) e = launch_gemm_inst<128, true>(ma, mb, args, grid, stream);
+        else if (L.bn == 256) e = pair ? launch_gemm_inst<256, true, true>(ma, mb, args, grid, stream)
+                                       : launch_gemm_inst<256, true>(ma, mb, args, grid, stream);
         else { if (err) *err = "unsupported BN"; return false; }
     }
     if (e != cudaSuccess) {
