@@ -25,6 +25,8 @@ Engine::~Engine() {
     if (step_graph) cudaGraphExecDestroy(step_graph);
     if (own_stream) cudaStreamDestroy(own_stream);
     if (side_stream) cudaStreamDestroy(side_stream);
+    if (mod_stream) cudaStreamDestroy(mod_stream);
+    if (ev_mod) cudaEventDestroy(ev_mod);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     free_plan();
@@ -67,6 +69,10 @@ foley_status Engine::create(const foley_config* c, int dev) {
     num_sms = prop.multiProcessorCount;
     FOLEY_CUDA_OK(cudaStreamCreate(&own_stream));
     FOLEY_CUDA_OK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    FOLEY_CUDA_OK(cudaStreamCreateWithFlags(&mod_stream, cudaStreamNonBlocking));
+    FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_mod, cudaEventDisableTiming));
+    if (const char* e = getenv("FOLEY_MOD_BRANCH")) mod_on_branch = atoi(e) != 0;
+    if (const char* e = getenv("FOLEY_PLAN")) sscanf(e, "%lf,%lf,%lf,%lf", &plan_tkb128, &plan_tkb256, &plan_tfix, &plan_tsplit);
     FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     {
@@ -375,13 +381,13 @@ void Engine::plan_gemm(int rows, int batch, int n, int kblocks, bool can_split, 
     const int smax = can_split ? std::min(max_splits, max_splits_used) : 1;
     for (int bn : {128, 256}) {
         const long long n_tiles = (n + bn - 1) / bn;
-        const double t_kb = bn == 128 ? 0.30 : 0.38;
+        const double t_kb = bn == 128 ? plan_tkb128 : plan_tkb256;
         for (int s = 1; s <= smax; ++s) {
             if (s > 1 && kblocks / s < 4) break;
             const long long ctas = m_tiles * n_tiles * s;
             const long long waves = (ctas + num_sms - 1) / num_sms;
             const int kb_per = (kblocks + s - 1) / s;
-            const double t = waves * (kb_per * t_kb + 5.0) + (s - 1) * 0.4;   // extra partials cost a little downstream
+            const double t = waves * (kb_per * t_kb + plan_tfix) + (s - 1) * plan_tsplit;   // extra partials cost a little downstream
             if (t < best - 1e-9) { best = t; best_bn = bn; best_s = s; }
         }
     }
@@ -643,14 +649,22 @@ foley_status Engine::step(cudaStream_t st) {
         return FOLEY_OK;
     };
 
-    // ---- single-block modulations for this step: x-independent, one GEMM for all NS blocks
+    // ---- single-block modulations for this step: x-independent, one GEMM for all NS blocks.  It only has to be ready
+    // before the first single block, so it runs on its own graph branch underneath the triple-stream phase.
+    const bool mod_branch = mod_on_branch && NT > 0;
+    cudaStream_t sm_ = mod_branch ? mod_stream : st;
     {
+        if (mod_branch) {
+            FOLEY_CUDA_OK(cudaEventRecord(ev_fork, st));
+            FOLEY_CUDA_OK(cudaStreamWaitEvent(sm_, ev_fork, 0));
+        }
         const long long n4 = static_cast<long long>(G) * L * C / 4;
-        FOLEY_CUDA_OK(launch_k(vectok_silu_kernel, dim3(blocks_for(n4, 256)), dim3(256), 0, st, a_sync, vec_all, cond_of_grp,
+        FOLEY_CUDA_OK(launch_k(vectok_silu_kernel, dim3(blocks_for(n4, 256)), dim3(256), 0, sm_, a_sync, vec_all, cond_of_grp,
                                trow_of_grp, G, L, C, vectok_act));
         ++launches;
-        ST_OK(gemm(st, vectok_act, G * L, 1, C, 0, mod_single_all, 0, NS * 6 * C,
+        ST_OK(gemm(sm_, vectok_act, G * L, 1, C, 0, mod_single_all, 0, NS * 6 * C,
                    bf(mod_single, ms_tok, mod_single_all.b, 0), 1, 256));
+        if (mod_branch) FOLEY_CUDA_OK(cudaEventRecord(ev_mod, sm_));
     }
     // The visual stream (B2*Lv = 80 rows at 5 s) is pure launch/latency overhead next to the audio stream: run it on a
     // side stream (a parallel branch of the captured graph) and meet only at the two attention calls of a block.
@@ -748,6 +762,7 @@ foley_status Engine::step(cudaStream_t st) {
             ST_OK(proj_combine(sv, attn_out, Lv, B2, C, jb, w.cross_proj[1], part_v, cv));
         }
         // -- MLPs
+        if (mod_branch && i == NT - 1) FOLEY_CUDA_OK(cudaStreamWaitEvent(st, ev_mod, 0));   // next: LN-modulate with single-block params
         ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.fc1[0], 0, F, bf(mlp_a, F, w.fc1[0].b, ACT_GELU_TANH), 1, pick_bn(L, B2, F, C / 64)));
         ST_OK(gemm(sv, h_v, RV, 1, C, 0, w.fc1[1], 0, F, bf(mlp_v, F, w.fc1[1].b, ACT_GELU_TANH), 1, 64));
         {

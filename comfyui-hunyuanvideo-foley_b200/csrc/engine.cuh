@@ -94,6 +94,10 @@ class Engine {
     int cur_G = 1;
     int num_sms = 148;
     cudaStream_t side_stream = nullptr;  // visual-stream branch of the step
+    cudaStream_t mod_stream = nullptr;   // single-block modulation GEMM branch
+    cudaEvent_t ev_mod = nullptr;
+    bool mod_on_branch = false;          // measured: no gain (the GEMM saturates the SMs either way)
+    double plan_tkb128 = 0.30, plan_tkb256 = 0.38, plan_tfix = 5.0, plan_tsplit = 0.4;   // planner cost model (us)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t own_stream = nullptr;   // blocking stream used when the caller passes NULL (legacy stream cannot be captured)
     // scratch of set_conditions / prepare_timesteps (plan-owned)

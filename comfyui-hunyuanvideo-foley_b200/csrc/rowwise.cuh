@@ -93,13 +93,24 @@ __device__ __forceinline__ float block_sum(float v, float* scratch /*[16]*/) {
 // vector and a 500-row call still puts ~40 warps on every SM (the first version used one warp per row and was
 // latency-bound at 27 us per call, 30 % of the step; profiles/r01_launches_xl_v1.txt).
 __global__ void __launch_bounds__(512) combine_ln_mod_kernel(const CombineArgs a) {
-    pdl_wait();
-    pdl_trigger();
     __shared__ float red0[16], red1[16];
     const int row = blockIdx.x;
     const int b = row / a.rm.L, l = row - b * a.rm.L;
     const int C = a.C;
     const int c = threadIdx.x * 4;
+    // Everything that does not depend on the predecessor kernel (bias, gate, shift, scale: weights or modulation
+    // vectors produced much earlier in the step) is fetched before the programmatic-dependency wait.
+    float bv[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {1.f, 1.f, 1.f, 1.f}, sv[4], cv[4];
+    const bool has_part = a.partials != nullptr;
+    if (has_part && a.bias) load_bf16x4(a.bias + c, bv);
+    if (has_part && a.gate.base) load_bf16x4(mod_ptr(a.gate, a.rm, b, l, a.gate_chunk, C) + c, gv);
+    const bool has_mod = a.h != nullptr && a.mod.base != nullptr;
+    if (has_mod) {
+        load_bf16x4(mod_ptr(a.mod, a.rm, b, l, a.shift_chunk, C) + c, sv);
+        load_bf16x4(mod_ptr(a.mod, a.rm, b, l, a.scale_chunk, C) + c, cv);
+    }
+    pdl_wait();
+    pdl_trigger();
     float x[4];
     float* xrow = a.x + static_cast<long long>(row) * C;
 
@@ -111,25 +122,18 @@ __global__ void __launch_bounds__(512) combine_ln_mod_kernel(const CombineArgs a
         x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
     }
 
-    if (a.partials) {
+    if (has_part) {
         const float* pr = a.partials + static_cast<long long>(row) * C + c;
         float4 acc = *reinterpret_cast<const float4*>(pr);
+#pragma unroll 4
         for (int s = 1; s < a.splits; ++s) {
             const float4 p = *reinterpret_cast<const float4*>(pr + s * a.split_stride);
             acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
         }
-        float y[4] = {acc.x, acc.y, acc.z, acc.w};
-        if (a.bias) {
-            float bv[4];
-            load_bf16x4(a.bias + c, bv);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) y[j] += bv[j];
-        }
+        float y[4] = {acc.x + bv[0], acc.y + bv[1], acc.z + bv[2], acc.w + bv[3]};
 #pragma unroll
         for (int j = 0; j < 4; ++j) y[j] = bf16_round(y[j]);
         if (a.gate.base) {
-            float gv[4];
-            load_bf16x4(mod_ptr(a.gate, a.rm, b, l, a.gate_chunk, C) + c, gv);
 #pragma unroll
             for (int j = 0; j < 4; ++j) y[j] = bf16_round(y[j] * gv[j]);
         }
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(512) combine_ln_mod_kernel(const CombineArgs a
             if (a.round_x) x[j] = bf16_round(x[j]);
         }
     }
-    if (a.partials || a.x_init) *reinterpret_cast<float4*>(xrow + c) = make_float4(x[0], x[1], x[2], x[3]);
+    if (has_part || a.x_init) *reinterpret_cast<float4*>(xrow + c) = make_float4(x[0], x[1], x[2], x[3]);
 
     if (a.h) {
         // two-pass LayerNorm in fp32 (mean, then centred second moment), like ATen's CUDA kernel
@@ -151,10 +155,7 @@ __global__ void __launch_bounds__(512) combine_ln_mod_kernel(const CombineArgs a
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = x[j] * rstd;
-        if (a.mod.base) {
-            float sv[4], cv[4];
-            load_bf16x4(mod_ptr(a.mod, a.rm, b, l, a.shift_chunk, C) + c, sv);
-            load_bf16x4(mod_ptr(a.mod, a.rm, b, l, a.scale_chunk, C) + c, cv);
+        if (has_mod) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = __fadd_rn(__fmul_rn(o[j], bf16_round(1.0f + cv[j])), sv[j]);
         }
@@ -192,32 +193,37 @@ struct QkvArgs {
 };
 
 __global__ void __launch_bounds__(128) qk_norm_rope_kernel(const QkvArgs a) {
-    pdl_wait();
-    pdl_trigger();
     const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int per_row = a.n_parts * a.H;
-    if (w >= a.rows_total * per_row) return;
-    const int row = w / per_row;
-    const int ph = w - row * per_row;
+    const bool active = w < a.rows_total * per_row;
+    const int row = active ? w / per_row : 0;
+    const int ph = active ? w - row * per_row : 0;
     const int part = ph / a.H, head = ph - part * a.H;
     const int b = row / a.L, l = row - b * a.L;
     const QkvPart& p = a.part[part];
+    // norm weights and RoPE tables are static: fetch them before the programmatic-dependency wait
+    float wv[4] = {1.f, 1.f, 1.f, 1.f};
+    float4 c = make_float4(1.f, 1.f, 1.f, 1.f), s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active && p.norm_w) {
+        load_bf16x4(p.norm_w + lane * 4, wv);
+        const int prow = a.pos ? a.pos[l] : l;
+        c = *reinterpret_cast<const float4*>(a.cos + static_cast<long long>(prow) * 128 + lane * 4);
+        s = *reinterpret_cast<const float4*>(a.sin + static_cast<long long>(prow) * 128 + lane * 4);
+    }
+    pdl_wait();
+    pdl_trigger();
+    if (!active) return;
     float v[4];
     load_bf16x4(a.src + static_cast<long long>(row) * a.src_ld + p.src_col + head * 128 + lane * 4, v);
     if (p.norm_w) {
         const float ss = warp_sum(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
         const float rstd = rsqrtf(ss * (1.0f / 128.0f) + a.eps);
-        float wv[4];
-        load_bf16x4(p.norm_w + lane * 4, wv);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (a.norm_kind == 0) v[j] = bf16_round(bf16_round(v[j] * rstd) * wv[j]);
             else v[j] = bf16_round(__fmul_rn(__fmul_rn(v[j], rstd), wv[j]));
         }
-        const int prow = a.pos ? a.pos[l] : l;
-        const float4 c = *reinterpret_cast<const float4*>(a.cos + static_cast<long long>(prow) * 128 + lane * 4);
-        const float4 s = *reinterpret_cast<const float4*>(a.sin + static_cast<long long>(prow) * 128 + lane * 4);
         // (x0, x1) -> (x0*cos - x1*sin, x1*cos + x0*sin)   (attn_layers.py:112-148)
         const float o0 = __fadd_rn(__fmul_rn(v[0], c.x), __fmul_rn(-v[1], s.x));
         const float o1 = __fadd_rn(__fmul_rn(v[1], c.y), __fmul_rn(v[0], s.y));

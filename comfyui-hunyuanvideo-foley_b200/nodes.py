@@ -237,7 +237,7 @@ class HunyuanFoleySampler:
                 "negative_prompt": ("STRING", {"multiline": True, "default": "noisy, harsh"}),
                 "cfg_scale": ("FLOAT", {"default": 4.5, "min": 1.0, "max": 10.0, "step": 0.1, "tooltip": "Classifier-Free Guidance scale"}),
                 "steps": ("INT", {"default": 50, "min": 10, "max": 100, "step": 1, "tooltip": "Number of denoising steps"}),
-                "sampler": (cls.SAMPLER_NAMES, {"default": "euler", "tooltip": "Flow-matching ODE solver; the B200 engine implements euler"}),
+                "sampler": (cls.SAMPLER_NAMES, {"default": "euler", "tooltip": "Flow-matching ODE solver; euler runs fully inside the B200 engine (one CUDA graph per step)"}),
                 "batch_size": ("INT", {"default": 1, "min": 1, "max": 64, "step": 1, "tooltip": "Number of audio variations to generate at once"}),
                 "seed": ("INT", {"default": 0, "min": 0, "max": 0xffffffffffffffff}),
                 "force_offload": ("BOOLEAN", {"default": True, "tooltip": "Accepted for compatibility; the engine keeps weights resident"}),

@@ -29,6 +29,67 @@ def sigma_schedule(num_inference_steps, shift=1.0):
     return sigmas
 
 
+class FlowMatchSolverState:
+    """The reference scheduler's `step` for its four solvers (scheduling_flow_match_discrete.py:210-373), quirk
+    included: heun-2 / midpoint-2 / kutta-4 treat consecutive calls as inner stages, `step_index` (so sigma and
+    sigma_next) only advances after the last stage, while the caller keeps feeding the next `timesteps` entry to the
+    model.  Euler runs inside the engine (foley_denoise); the multi-stage solvers use this host state machine around
+    foley_dit_forward."""
+
+    STAGES = {"euler": 1, "heun-2": 2, "midpoint-2": 2, "kutta-4": 4}
+
+    def __init__(self, solver, sigmas):
+        self.solver, self.sigmas = solver, sigmas.float()
+        self.step_index = 0
+        self.derivatives, self.dt, self.sample = [], None, None
+
+    def step(self, model_output, sample):
+        mo, sample = model_output.float(), sample.float()
+        sigma, sigma_next = float(self.sigmas[self.step_index]), float(self.sigmas[self.step_index + 1])
+        dt_full = torch.tensor(sigma_next, dtype=torch.float32) - torch.tensor(sigma, dtype=torch.float32)
+        stage, n_stages = len(self.derivatives), self.STAGES[self.solver]
+        if n_stages == 1:
+            derivative, dt, last = mo, dt_full, True
+        elif stage == 0:
+            self.derivatives, self.dt, self.sample = [mo], dt_full, sample
+            derivative, last = mo, False
+            dt = self.dt if self.solver == "heun-2" else self.dt / 2
+        elif stage < n_stages - 1:
+            self.derivatives.append(mo)
+            derivative, last = mo, False
+            dt = self.dt / 2 if stage == 1 else self.dt
+        else:
+            d = self.derivatives
+            if self.solver == "heun-2":
+                derivative = 0.5 * (d[0] + mo)
+            elif self.solver == "midpoint-2":
+                derivative = mo
+            else:
+                derivative = 1 / 6 * d[0] + 1 / 3 * d[1] + 1 / 3 * d[2] + 1 / 6 * mo
+            dt, sample, last = self.dt, self.sample, True
+            self.derivatives, self.dt, self.sample = [], None, None
+        if last:
+            self.step_index += 1
+        return sample + derivative * dt.to(sample.device)
+
+
+def _denoise_multistage(engine, latents, sigmas, guidance_scale, solver, n_cond, progress):
+    """utils.py:203-247 for the multi-stage solvers: one foley_dit_forward per `timesteps` entry."""
+    timesteps = (sigmas[:-1] * 1000).to(torch.float32)
+    state = FlowMatchSolverState(solver, sigmas)
+    lat = latents.float()
+    for i in range(timesteps.numel()):
+        x = torch.cat([lat] * 2) if n_cond == 2 else lat
+        out = engine.dit_forward(x, float(timesteps[i]))          # fp32 tensor holding the bf16 model output
+        if n_cond == 2:
+            u, c = out.bfloat16().chunk(2)
+            out = (u + guidance_scale * (c - u)).float()          # bf16 arithmetic, utils.py:241-243
+        lat = state.step(out, lat)
+        if progress is not None:
+            progress(i + 1)
+    return lat
+
+
 def _pad_or_trim_time(x, T_fixed):
     """utils.py:104-111."""
     T_cur = x.shape[1]
@@ -68,9 +129,6 @@ def denoise_process_with_generator(visual_feats, text_feats, audio_len_in_s, mod
     noise draw — the multi-GPU sharding hook; the reference has no equivalent."""
     if sampler not in SOLVERS:
         raise ValueError(f"Solver {sampler} not supported. Supported solvers: {list(SOLVERS)}")
-    if sampler != "euler":
-        raise NotImplementedError("foley_b200 implements the benchmarked Euler solver; heun-2 / midpoint-2 / "
-                                  "kutta-4 are listed as next scope (SURVEY.md §8f)")
     foley_model = model_dict.foley_model
     engine = foley_model.engine
     device = model_dict.device
@@ -110,7 +168,11 @@ def denoise_process_with_generator(visual_feats, text_feats, audio_len_in_s, mod
     pbar = ProgressBar(num_inference_steps)
     progress = (lambda step: pbar.update(1)) if model_dict.get("report_progress", True) else None
     with torch.inference_mode():
-        latents = engine.denoise(latents.to(device), sigmas, guidance_scale, progress=progress)
+        if sampler == "euler":     # the benchmarked solver: whole loop inside the engine, one CUDA graph per step
+            latents = engine.denoise(latents.to(device), sigmas, guidance_scale, progress=progress)
+        else:
+            latents = _denoise_multistage(engine, latents.to(device), sigmas, guidance_scale, sampler,
+                                          2 if guidance_scale > 1.0 else 1, progress)
         if not decode:
             return latents, model_dict.dac_model.sample_rate if "dac_model" in model_dict else 48000
         audio = model_dict.dac_model.decode(latents)

@@ -314,14 +314,58 @@ def build_cfg_batch(sd, feats, batch, guidance, T=77):
     return clip, sync, text
 
 
-def denoise(sd, cfg, feats, latents, n_steps, guidance, policy="fp32", step_callback=None):
-    """denoise_process_with_generator's loop (utils.py:203-247) with the Euler solver
-    (scheduling_flow_match_discrete.py:262-297).  latents [B,128,L] initial noise -> final latents (fp32)."""
+class SolverState:
+    """FlowMatchDiscreteScheduler.step for all four solvers (scheduling_flow_match_discrete.py:210-373), including
+    its quirk: the multi-stage solvers treat consecutive `step()` calls as *inner* stages — the caller keeps feeding
+    the next entry of `timesteps` to the model while `step_index` (hence sigma, sigma_next) only advances after the
+    last stage, so N calls perform N/2 (heun-2, midpoint-2) or N/4 (kutta-4) real steps."""
+
+    STAGES = {"euler": 1, "heun-2": 2, "midpoint-2": 2, "kutta-4": 4}
+
+    def __init__(self, solver, sigmas):
+        if solver not in self.STAGES:
+            raise ValueError(f"Solver {solver} not supported. Supported solvers: {list(self.STAGES)}")
+        self.solver, self.sigmas = solver, sigmas.float()
+        self.step_index = 0
+        self.d, self.dt, self.sample = [], None, None
+
+    def step(self, model_output, sample):
+        mo, sample = model_output.float(), sample.float()
+        sigma, sigma_next = self.sigmas[self.step_index], self.sigmas[self.step_index + 1]
+        stage, n_stages = len(self.d), self.STAGES[self.solver]
+        if n_stages == 1:
+            derivative, dt, last = mo, sigma_next - sigma, True
+        elif stage == 0:
+            self.d, self.dt, self.sample = [mo], sigma_next - sigma, sample
+            derivative, last = mo, False
+            dt = self.dt if self.solver == "heun-2" else self.dt / 2
+        elif stage < n_stages - 1:                 # kutta-4 stages 2 and 3
+            self.d.append(mo)
+            derivative, last = mo, False
+            dt = self.dt / 2 if stage == 1 else self.dt
+        else:
+            if self.solver == "heun-2":
+                derivative = 0.5 * (self.d[0] + mo)
+            elif self.solver == "midpoint-2":
+                derivative = mo
+            else:
+                derivative = 1 / 6 * self.d[0] + 1 / 3 * self.d[1] + 1 / 3 * self.d[2] + 1 / 6 * mo
+            dt, sample, last = self.dt, self.sample, True
+            self.d, self.dt, self.sample = [], None, None
+        if last:
+            self.step_index += 1
+        return sample + derivative * dt
+
+
+def denoise(sd, cfg, feats, latents, n_steps, guidance, policy="fp32", step_callback=None, solver="euler"):
+    """denoise_process_with_generator's loop (utils.py:203-247) with the scheduler's step
+    (scheduling_flow_match_discrete.py:210-373).  latents [B,128,L] initial noise -> final latents (fp32)."""
     p = policy if isinstance(policy, Policy) else Policy(policy)
     B = latents.shape[0]
     clip, sync, text = build_cfg_batch(sd, feats, B, guidance)
     sig = sigma_schedule(n_steps)
     ts = (sig[:-1] * 1000).float()
+    state = SolverState(solver, sig)
     lat = p.r(latents.float())      # noise is drawn in the model dtype (utils.py:151-156)
     for i in range(n_steps):
         x = torch.cat([lat] * 2) if guidance > 1.0 else lat
@@ -330,7 +374,7 @@ def denoise(sd, cfg, feats, latents, n_steps, guidance, policy="fp32", step_call
         if guidance > 1.0:
             u, c = out.chunk(2)
             out = p.r(u + p.r(guidance * p.r(c - u)))              # utils.py:241-243 (model dtype)
-        lat = lat.float() + out.float() * (sig[i + 1] - sig[i])    # fp32 Euler update
+        lat = state.step(out, lat)                                 # fp32 update
         if step_callback is not None:
             step_callback(i, lat)
     return lat

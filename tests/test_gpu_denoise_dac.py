@@ -125,5 +125,30 @@ def test_sampler_node_end_to_end(golden_dir):
     r = rel_l2(batch["waveform"], gold["audio"].float())
     print(f"\nSampler node waveform vs reference: {r:.3e}")
     assert r <= 1e-2
-    with pytest.raises(NotImplementedError):
-        nodes.HunyuanFoleySampler().generate_audio(model, deps, 8.0, 1.0, "p", "n", 1.0, 10, "heun-2", 1, 0, True)
+    with pytest.raises(ValueError):
+        nodes.HunyuanFoleySampler().generate_audio(model, deps, 8.0, 1.0, "p", "n", 1.0, 10, "dpm++", 1, 0, True)
+
+
+@pytest.mark.parametrize("tag", ["tiny_heun2", "tiny_midpoint2", "tiny_kutta4"])
+def test_multistage_solvers_match_reference(golden_dir, tag):
+    """heun-2 / midpoint-2 / kutta-4 (reference scheduler :299-373 incl. its inner-stage quirk) through the public
+    host function, against the reference's own run."""
+    nodes, cfgmod, sampling = load_pkg("nodes"), load_pkg("config"), load_pkg("sampling")
+    gold = torch.load(os.path.join(golden_dir, f"denoise_{tag}.pt"))
+    a = gold["args"]
+    eng, c, sd = make_engine("tiny")
+    cfg = cfgmod.load_model_config("xxl")
+    model = nodes.FoleyModel(eng, sd["empty_clip_feat"], sd["empty_sync_feat"], cfg, dtype=torch.float32)
+    feats, L, Lv, S = _feats(c, sd, a["duration"], a["v2a"])
+    visual = {"siglip2_feat": feats["siglip2_feat"], "syncformer_feat": feats["syncformer_feat"]}
+    text = {"text_feat": feats["text_feat"], "uncond_text_feat": feats["uncond_text_feat"]}
+    md = cfgmod.AttributeDict({"foley_model": model, "device": torch.device("cuda", 0)})
+    gen = torch.Generator(device="cpu").manual_seed(123)
+    lat, _ = sampling.denoise_process_with_generator(visual, text, a["duration"], md, cfg, a["guidance"], a["steps"],
+                                                     a["batch"], a["sampler"], generator=gen, decode=False)
+    noise = torch.randn((a["batch"], 128, L), generator=torch.Generator(device="cpu").manual_seed(123))
+    want16 = O.denoise(sd, c, feats, noise, a["steps"], a["guidance"], policy="cuda_bf16", solver=a["sampler"])
+    gap = rel_l2(want16, gold["latents"])
+    r16, r32 = rel_l2(lat.cpu(), want16), rel_l2(lat.cpu(), gold["latents"])
+    print(f"\n[{tag}] engine vs oracle(cuda_bf16) {r16:.3e} | vs reference fp32 {r32:.3e} | oracle gap {gap:.3e}")
+    assert r16 <= 1.5 * gap + 1e-3 and r32 <= 1.5 * gap + 1e-3

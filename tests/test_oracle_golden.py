@@ -52,7 +52,7 @@ def test_bf16_policy_is_closer_to_bf16_reference_than_fp32_is(golden_dir):
     assert rel_l2(out, g16["out"]) < 0.5 * gap_ref
 
 
-@pytest.mark.parametrize("tag", ["tiny_t2a_nocfg", "tiny_v2a_cfg"])
+@pytest.mark.parametrize("tag", ["tiny_t2a_nocfg", "tiny_v2a_cfg", "tiny_heun2", "tiny_midpoint2", "tiny_kutta4"])
 def test_denoise_loop_and_decode_match_reference(golden_dir, tag):
     gold = torch.load(os.path.join(golden_dir, f"denoise_{tag}.pt"))
     a = gold["args"]
@@ -65,7 +65,7 @@ def test_denoise_loop_and_decode_match_reference(golden_dir, tag):
         feats["syncformer_feat"] = sd["empty_sync_feat"][None].expand(1, S, -1)
     gen = torch.Generator(device="cpu").manual_seed(123)
     noise = torch.randn((a["batch"], 128, L), generator=gen, dtype=torch.float32)
-    lat = O.denoise(sd, c, feats, noise, a["steps"], a["guidance"], policy="fp32")
+    lat = O.denoise(sd, c, feats, noise, a["steps"], a["guidance"], policy="fp32", solver=a.get("sampler", "euler"))
     assert rel_l2(lat, gold["latents"]) <= 2e-5
     dsd = W.synth_dac_state_dict(W.DAC_TINY, seed=3)
     wav = O.dac_decode(dsd, lat)

@@ -120,7 +120,7 @@ def small_dac(ns, dcfg):
     return dac.eval().float()
 
 
-def gold_denoise(ns, tag, duration, steps, guidance, batch, v2a):
+def gold_denoise(ns, tag, duration, steps, guidance, batch, v2a, sampler="euler"):
     name = "tiny"
     c = W.model_config(name)
     model, cfg, sd = build_ref_model(ns, name, torch.float32)
@@ -145,10 +145,10 @@ def gold_denoise(ns, tag, duration, steps, guidance, batch, v2a):
     gen = torch.Generator(device="cpu").manual_seed(123)
     audio, sr = ns.utils.denoise_process_with_generator(visual, text, duration, md, cfg, guidance_scale=guidance,
                                                         num_inference_steps=steps, batch_size=batch,
-                                                        sampler="euler", generator=gen)
+                                                        sampler=sampler, generator=gen)
     path = os.path.join(GOLD, f"denoise_{tag}.pt")
     torch.save({"latents": captured["latents"].float(), "audio": audio.float().half(), "sr": sr,
-                "args": dict(duration=duration, steps=steps, guidance=guidance, batch=batch, v2a=v2a)}, path)
+                "args": dict(duration=duration, steps=steps, guidance=guidance, batch=batch, v2a=v2a, sampler=sampler)}, path)
     print("wrote", path, tuple(captured["latents"].shape), tuple(audio.shape))
 
 
@@ -179,6 +179,9 @@ def main():
         "dit_small_cudabf16": lambda: gold_dit(ns, "small", "small_cudabf16", 2, 125, 20, 48, "cuda_bf16"),
         "denoise_t2a": lambda: gold_denoise(ns, "tiny_t2a_nocfg", 1.0, 10, 1.0, 1, False),
         "denoise_v2a": lambda: gold_denoise(ns, "tiny_v2a_cfg", 1.0, 4, 4.5, 2, True),
+        "denoise_heun": lambda: gold_denoise(ns, "tiny_heun2", 1.0, 6, 4.5, 1, True, "heun-2"),
+        "denoise_midpoint": lambda: gold_denoise(ns, "tiny_midpoint2", 1.0, 6, 1.0, 1, True, "midpoint-2"),
+        "denoise_kutta": lambda: gold_denoise(ns, "tiny_kutta4", 1.0, 8, 4.5, 1, True, "kutta-4"),
         "dac_full": lambda: gold_dac_full(ns),
     }
     for k, fn in jobs.items():
