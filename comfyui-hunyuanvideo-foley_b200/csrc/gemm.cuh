@@ -117,6 +117,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const uint32_t pair_rank = kPair ? cluster_ctarank() : 0;
     const bool leader = pair_rank == 0;
 
+    // Each CTA's loads complete on its OWN full barrier; in pair mode the peer forwards "stage landed" to the leader
+    // with one remote arrive per stage (remote complete_tx from TMA, the cta_group::2 TMA form, measured slower here).
+    auto load_b = [&](int i) {
+        const int s = i % Cfg::STAGES;
+        const int kb = kb_begin + i;
+        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        tma_load_3d(smem_b + s * Cfg::B_BYTES, &tm_b, &full_bar[s], kb * Cfg::BK,
+                    n0 + static_cast<int>(pair_rank) * Cfg::B_ROWS, 0);   // rank-3 map; pair: this CTA's half
+    };
+    const int pre = g.dbg_stop == 1 ? 0 : (num_kb < Cfg::STAGES ? num_kb : Cfg::STAGES);
+
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
         tma_prefetch_desc(&tm_b);
@@ -127,6 +138,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         }
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
+        // Weights do not depend on the previous kernel (programmatic dependent launch) nor on the TMEM allocation
+        // going on in warp 1: fill the ring with B tiles right away so the weight stream's latency hides under the
+        // rest of the prologue and under the predecessor kernel's tail.
+        for (int i = 0; i < pre; ++i) load_b(i);
     } else if (warp == 1) {
         if constexpr (kPair) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr_smem);
         else tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
@@ -142,16 +157,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     } else if (warp == 0) {
         // ------------------------------------------------------------- TMA producer
         if (lane == 0) {
-            // Each CTA's loads complete on its OWN full barrier; in pair mode the peer forwards "stage landed" to the
-            // leader with one remote arrive per stage (remote complete_tx from TMA, the cta_group::2 TMA form, measured
-            // 2.4x slower here).
-            auto load_b = [&](int i) {
-                const int s = i % Cfg::STAGES;
-                const int kb = kb_begin + i;
-                mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                tma_load_3d(smem_b + s * Cfg::B_BYTES, &tm_b, &full_bar[s], kb * Cfg::BK,
-                            n0 + static_cast<int>(pair_rank) * Cfg::B_ROWS, 0);   // rank-3 map; pair: this CTA's half
-            };
             auto load_a = [&](int i) {
                 const int s = i % Cfg::STAGES;
                 const int kb = kb_begin + i;
@@ -160,11 +165,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 const int arow = m0 + g.tap_off0 + tap * g.tap_stride;
                 tma_load_3d(smem_a + s * Cfg::A_BYTES, &tm_a, &full_bar[s], kcol, arow, batch);
             };
-            // Weights do not depend on the previous kernel: fill the ring with B tiles before waiting on it
-            // (programmatic dependent launch), so the weight stream's HBM latency hides under the predecessor.
-            const int pre = num_kb < Cfg::STAGES ? num_kb : Cfg::STAGES;
-            for (int i = 0; i < pre; ++i) load_b(i);
-            pdl_wait();
+            pdl_wait();   // activations (A) are the predecessor's output
             for (int i = 0; i < num_kb; ++i) {
                 if (i >= pre) {
                     const int s = i % Cfg::STAGES;
