@@ -27,10 +27,15 @@ struct AttnArgs {
     float scale_log2 = 0.f;                             // scale * log2(e)
 };
 
-constexpr int ATT_BM = 64, ATT_BN = 64, ATT_D = 128;
-constexpr int ATT_STAGES = 4;                                  // K/V tiles in flight (cp.async groups)
+constexpr int ATT_BN = 64, ATT_D = 128;
 constexpr int ATT_TILE = ATT_BN * ATT_D * 2;                   // 16 KB
-constexpr int ATT_SMEM = ATT_BM * ATT_D * 2 + ATT_STAGES * 2 * ATT_TILE;  // Q + 4 x (K, V) = 144 KB
+// Two shapes: 4 warps x 16 query rows with a 4-deep K/V ring (small grids: more CTAs, deeper prefetch) and 8 warps
+// x 16 rows with a 3-deep ring (large batches: twice the warps per SM, K/V tiles shared by twice the queries).
+template <int NW, int NST>
+struct AttCfg {
+    static constexpr int BM = 16 * NW;
+    static constexpr int SMEM = BM * ATT_D * 2 + NST * 2 * ATT_TILE;
+};
 
 __device__ __forceinline__ uint32_t swz(int row, int chunk) {  // byte offset of a 16-byte chunk in a [rows][128] bf16 tile
     return static_cast<uint32_t>(row * 256 + ((chunk ^ (row & 7)) << 4));
@@ -65,7 +70,10 @@ __device__ __forceinline__ void load_tile(uint32_t smem_base, const __nv_bfloat1
     }
 }
 
-__global__ void __launch_bounds__(128) attention_kernel(const AttnArgs a) {
+template <int NW, int NST>
+__global__ void __launch_bounds__(32 * NW) attention_kernel(const AttnArgs a) {
+    constexpr int ATT_BM = AttCfg<NW, NST>::BM;
+    constexpr int ATT_STAGES = NST;
     pdl_wait();
     pdl_trigger();
     extern __shared__ __align__(1024) uint8_t att_smem[];

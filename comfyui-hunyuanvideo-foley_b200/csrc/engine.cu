@@ -78,7 +78,8 @@ foley_status Engine::create(const foley_config* c, int dev) {
     {
         std::string err;
         if (!gemm_init_attributes(&err)) return fail(FOLEY_ERR_CUDA, err);
-        FOLEY_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        FOLEY_CUDA_OK(cudaFuncSetAttribute(attention_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<4, 4>::SMEM));
+        FOLEY_CUDA_OK(cudaFuncSetAttribute(attention_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<8, 3>::SMEM));
     }
     triple.resize(NT);
     single.resize(NS);
@@ -308,6 +309,7 @@ void Engine::free_plan() {
     plan_allocs.clear();
     plan = Plan();
     graph_valid = false;
+    tables_ready = false;
 }
 
 foley_status Engine::alloc_plan(int B, int U, int L, int Lv, int S, int T) {
@@ -514,14 +516,16 @@ foley_status Engine::set_conditions(const void* clip, const void* sync, const vo
     ST_OK(gemm(st, s1, US, 1, C, 0, sync_w13, 0, 2 * Hy, bf(s2, Hy, nullptr, 0, EPI_SWIGLU), 1, 128));
     ST_OK(gemm(st, s2, US, 1, Hy, 0, sync_w2, 0, C, bf(s3, C, nullptr, 0), 1, 128));
     {
-        std::vector<int> idx = nearest_exact_index(S, L);
-        FOLEY_CUDA_OK(cudaMemcpyAsync(idx_dev, idx.data(), L * sizeof(int), cudaMemcpyHostToDevice, st));
-        FOLEY_CUDA_OK(cudaStreamSynchronize(st));
+        if (!tables_ready) {   // index / RoPE tables depend only on the plan's shapes: built once per plan
+            std::vector<int> idx = nearest_exact_index(S, L);
+            FOLEY_CUDA_OK(cudaMemcpyAsync(idx_dev, idx.data(), L * sizeof(int), cudaMemcpyHostToDevice, st));
+            FOLEY_CUDA_OK(cudaStreamSynchronize(st));
+        }
         gather_rows_kernel<<<blocks_for(static_cast<long long>(U) * L * C / 8, 256), 256, 0, st>>>(s3, idx_dev, U, S, L, C, a_sync);
         ++launches;
     }
     // ---- RoPE tables (hifi_foley.py:797-803, 151-166, 865; positions per oracle.interleaved_positions)
-    {
+    if (!tables_ready) {
         std::vector<int> pa(L), pv(Lv), pp(std::max(L, std::max(Lv, T)));
         std::vector<int> pick = nearest_exact_index(L, Lv);
         for (int i = 0; i < L; ++i) pa[i] = 2 * i;
@@ -538,6 +542,7 @@ foley_status Engine::set_conditions(const void* clip, const void* sync, const vo
         ST_OK(up(pa, rope_av_a_cos, rope_av_a_sin));
         ST_OK(up(pv, rope_av_v_cos, rope_av_v_sin));
         ST_OK(up(pp, rope_plain_cos, rope_plain_sin));
+        tables_ready = true;
     }
     // ---- text branch: cond_in, then K/V of every triple block at once (step-invariant, hifi_foley.py:289-308)
     ST_OK(gemm(st, text_b, UT, 1, cfg.text_dim, 0, cond1, 0, C, bf(c1, C, cond1.b, ACT_SILU), 1, 128));
@@ -643,8 +648,14 @@ foley_status Engine::step(cudaStream_t st) {
         a.kv_batch_map = cross ? cond_of_grp : nullptr;
         a.grp_of_sample = cross ? grp_of_sample : nullptr;
         a.scale_log2 = 1.4426950408889634f / sqrtf(128.0f);
-        dim3 grid((Sq + ATT_BM - 1) / ATT_BM, H, B2);
-        FOLEY_CUDA_OK(launch_k(attention_kernel, grid, dim3(128), ATT_SMEM, st, a));
+        const long long ctas64 = static_cast<long long>((Sq + 63) / 64) * H * B2;
+        if (ctas64 > 2LL * num_sms) {
+            dim3 grid((Sq + 127) / 128, H, B2);
+            FOLEY_CUDA_OK(launch_k(attention_kernel<8, 3>, grid, dim3(256), AttCfg<8, 3>::SMEM, st, a));
+        } else {
+            dim3 grid((Sq + 63) / 64, H, B2);
+            FOLEY_CUDA_OK(launch_k(attention_kernel<4, 4>, grid, dim3(128), AttCfg<4, 4>::SMEM, st, a));
+        }
         ++launches;
         return FOLEY_OK;
     };

@@ -88,6 +88,7 @@ class Engine {
     int max_splits_used = 8;     // runtime cap (<= max_splits)
     cudaGraphExec_t step_graph = nullptr;
     bool graph_valid = false;
+    bool tables_ready = false;   // RoPE / nearest-exact tables of the current plan uploaded
     bool use_cuda_graph = true;
     float graph_guidance = 0.f;
     int64_t graph_launches_per_step = 0;

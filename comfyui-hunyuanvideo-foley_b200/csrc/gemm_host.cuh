@@ -222,7 +222,7 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
     // CTA-pair (cta_group::2) tiles: need an even number of m-tiles and a 128/256-wide tile
     int pair = L.pair >= 0 ? L.pair : default_pair_mode();
     if (mt % 2 != 0 || (L.bn != 256 && L.bn != 128) || (tf32 && L.bn != 256)) pair = 0;
-    const int cx = 1, cy = 1;
+    const int cy = 1;
     CUtensorMap ma, mb;
     if (!encode_operand_map(&ma, L.a, 128 / cy, err)) return false;
     Operand wb;

@@ -90,17 +90,6 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-// Multicast variant: the tile lands at the same shared-memory offset of every CTA in `cta_mask` (bit = rank in
-// cluster) and completes `bytes` on the mbarrier at the same offset in each of them.
-__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                               int c2, uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-        " [%0], [%1, {%4, %5, %6}], [%2], %3;"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(cta_mask),
-          "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
 // ----------------------------------------------------------------------------- programmatic dependent launch
 // wait: blocks until the preceding kernel in the stream has completed and its writes are visible (no-op when the
 // kernel was not launched with the programmatic-serialization attribute).  trigger: lets the next kernel start
@@ -228,12 +217,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// Same, arriving on the barrier at this offset in every CTA of `cta_mask` (cluster-wide stage release).
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(cta_mask)
                  : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives TMEM lane (base_lane + i).
