@@ -115,7 +115,16 @@ extern "C" foley_status foley_denoise(foley_engine* e, float* latents, const flo
                                       float guidance, foley_progress_fn progress, void* user, void* stream) {
     if (!e || !latents || !sigmas) return fail(FOLEY_ERR_INVALID, "foley_denoise: null argument");
     API_GUARD_BEGIN
-    return e->impl.denoise(latents, sigmas, n_steps, guidance, progress, user, e->impl.pick_stream(stream));
+    return e->impl.denoise(latents, sigmas, n_steps, guidance, FOLEY_SOLVER_EULER, progress, user, e->impl.pick_stream(stream));
+    API_GUARD_END
+}
+
+extern "C" foley_status foley_denoise_solver(foley_engine* e, float* latents, const float* sigmas, int32_t n_calls,
+                                             float guidance, int32_t solver, foley_progress_fn progress, void* user,
+                                             void* stream) {
+    if (!e || !latents || !sigmas) return fail(FOLEY_ERR_INVALID, "foley_denoise_solver: null argument");
+    API_GUARD_BEGIN
+    return e->impl.denoise(latents, sigmas, n_calls, guidance, solver, progress, user, e->impl.pick_stream(stream));
     API_GUARD_END
 }
 

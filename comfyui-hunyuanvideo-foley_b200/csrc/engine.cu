@@ -368,6 +368,7 @@ foley_status Engine::alloc_plan(int B, int U, int L, int Lv, int S, int T) {
     plan = p;
     // group-dependent buffers are (re)sized by prepare_timesteps
     vectok_act = nullptr; mod_single = nullptr; vec_all = nullptr; mod_triple = nullptr; sigmas_dev = nullptr; t_dev = nullptr;
+    sol_d[0] = sol_d[1] = sol_d[2] = sol_samp = nullptr; sol_table = nullptr; sol_table_cap = 0;
     plan.n_t = 0;
     return FOLEY_OK;
 }
@@ -848,12 +849,64 @@ foley_status Engine::forward(const float* x, const float* t, int n_t, float* out
     return FOLEY_OK;
 }
 
-foley_status Engine::denoise(float* latents, const float* sigmas, int n_steps, float guidance,
+// Per-call stage table of the reference scheduler's multi-stage solvers (scheduling_flow_match_discrete.py:299-373).
+// Call i feeds timesteps[i] to the model (utils.py:215-246) while sigma / sigma_next come from `step_index`, which
+// only advances after a solver's last stage.
+static std::vector<SolverCall> solver_table(int solver, const float* sigmas, int n_calls) {
+    const int n_stages = solver == FOLEY_SOLVER_KUTTA4 ? 4 : 2;
+    std::vector<SolverCall> tab(n_calls);
+    int step_index = 0, stage = 0;
+    float dt_full = 0.f;
+    for (int i = 0; i < n_calls; ++i) {
+        SolverCall c{};
+        c.store_slot = -1;
+        if (stage == 0) {
+            dt_full = sigmas[step_index + 1] - sigmas[step_index];   // fp32, like the reference's tensors
+            c.save_sample = 1;
+            c.store_slot = 0;
+            c.dt = solver == FOLEY_SOLVER_HEUN2 ? dt_full : dt_full / 2;
+        } else if (stage < n_stages - 1) {   // kutta-4 stages 1, 2
+            c.store_slot = stage;
+            c.dt = stage == 1 ? dt_full / 2 : dt_full;
+        } else {
+            c.base_saved = 1;
+            c.dt = dt_full;
+            if (solver == FOLEY_SOLVER_HEUN2) c.kind = 1;
+            else if (solver == FOLEY_SOLVER_KUTTA4) {
+                c.kind = 2;
+                c.c0 = c.cm = static_cast<float>(1.0 / 6.0);
+                c.c1 = c.c2 = static_cast<float>(1.0 / 3.0);
+            }
+        }
+        tab[i] = c;
+        if (++stage == n_stages) { stage = 0; ++step_index; }
+    }
+    return tab;
+}
+
+foley_status Engine::denoise(float* latents, const float* sigmas, int n_steps, float guidance, int solver,
                              foley_progress_fn progress, void* user, cudaStream_t st) {
     if (!plan.valid) return fail(FOLEY_ERR_STATE, "foley_denoise before foley_set_conditions");
     if (n_steps < 1) return fail(FOLEY_ERR_INVALID, "n_steps < 1");
+    if (solver < FOLEY_SOLVER_EULER || solver > FOLEY_SOLVER_KUTTA4) return fail(FOLEY_ERR_INVALID, "unknown solver id");
     Plan& p = plan;
     FOLEY_CUDA_OK(cudaSetDevice(device));
+    if (solver != FOLEY_SOLVER_EULER) {
+        const size_t n = static_cast<size_t>(p.B) * LAT * p.L;
+        if (!sol_samp) {
+            for (int i = 0; i < 3; ++i) ST_OK(palloc(&sol_d[i], n));
+            ST_OK(palloc(&sol_samp, n));
+            graph_valid = false;
+        }
+        if (n_steps > sol_table_cap) {
+            ST_OK(palloc(&sol_table, static_cast<size_t>(n_steps)));
+            sol_table_cap = n_steps;
+            graph_valid = false;
+        }
+        const std::vector<SolverCall> tab = solver_table(solver, sigmas, n_steps);
+        FOLEY_CUDA_OK(cudaMemcpyAsync(sol_table, tab.data(), tab.size() * sizeof(SolverCall), cudaMemcpyHostToDevice, st));
+        FOLEY_CUDA_OK(cudaStreamSynchronize(st));   // `tab` goes out of scope
+    }
     std::vector<float> ts(n_steps);
     for (int i = 0; i < n_steps; ++i) ts[i] = sigmas[i] * 1000.0f;   // scheduler.timesteps (scheduling_...py:151)
     ST_OK(prepare_timesteps(ts.data(), n_steps, false, st));
@@ -867,8 +920,12 @@ foley_status Engine::denoise(float* latents, const float* sigmas, int n_steps, f
 
     auto body = [&]() -> foley_status {
         ST_OK(step(st));
-        FOLEY_CUDA_OK(launch_k(cfg_euler_kernel, grid, blk, 0, st, y_out, lat_dev, x_in, p.B, p.U, LAT, p.L, guidance,
-                               sigmas_dev, step_dev));
+        if (solver == FOLEY_SOLVER_EULER)
+            FOLEY_CUDA_OK(launch_k(cfg_euler_kernel, grid, blk, 0, st, y_out, lat_dev, x_in, p.B, p.U, LAT, p.L, guidance,
+                                   sigmas_dev, step_dev));
+        else   // the table entry decides the stage; the kernel itself is the same for every call and solver
+            FOLEY_CUDA_OK(launch_k(cfg_solver_kernel, grid, blk, 0, st, y_out, lat_dev, x_in, sol_d[0], sol_d[1], sol_d[2],
+                                   sol_samp, p.B, p.U, LAT, p.L, guidance, sol_table, step_dev));
         FOLEY_CUDA_OK(launch_k(advance_step_kernel, dim3(1), dim3(32), 0, st, step_dev, trow_of_grp, cur_G));
         launches += 2;
         FOLEY_CUDA_OK(cudaGetLastError());
@@ -876,7 +933,8 @@ foley_status Engine::denoise(float* latents, const float* sigmas, int n_steps, f
     };
     const bool use_graph = use_cuda_graph;
     int64_t per_step = 0;
-    if (use_graph && (!graph_valid || graph_guidance != guidance)) {
+    const bool solver_kind = solver != FOLEY_SOLVER_EULER;
+    if (use_graph && (!graph_valid || graph_guidance != guidance || graph_solver_kind != solver_kind)) {
         if (step_graph) { cudaGraphExecDestroy(step_graph); step_graph = nullptr; }
         const int64_t before = launches;
         cudaGraph_t g = nullptr;
@@ -892,6 +950,7 @@ foley_status Engine::denoise(float* latents, const float* sigmas, int n_steps, f
         launches = before;   // capture does not execute
         graph_valid = true;
         graph_guidance = guidance;
+        graph_solver_kind = solver_kind;
     }
     per_step = graph_launches_per_step;
     for (int i = 0; i < n_steps; ++i) {

@@ -91,6 +91,10 @@ class Engine {
     bool tables_ready = false;   // RoPE / nearest-exact tables of the current plan uploaded
     bool use_cuda_graph = true;
     float graph_guidance = 0.f;
+    bool graph_solver_kind = false;      // the captured step ends in cfg_solver_kernel instead of cfg_euler_kernel
+    float *sol_d[3] = {nullptr, nullptr, nullptr}, *sol_samp = nullptr;   // multi-stage solver state [B, latent, L] fp32
+    SolverCall* sol_table = nullptr;
+    int sol_table_cap = 0;
     int64_t graph_launches_per_step = 0;
     int cur_G = 1;
     int num_sms = 148;
@@ -125,7 +129,7 @@ class Engine {
     foley_status prepare_timesteps(const float* t_host, int n_t, bool per_sample, cudaStream_t st);
     foley_status step(cudaStream_t st);                 // one forward: x_in -> y_out
     foley_status forward(const float* x, const float* t, int n_t, float* out, cudaStream_t st);
-    foley_status denoise(float* latents, const float* sigmas, int n_steps, float guidance,
+    foley_status denoise(float* latents, const float* sigmas, int n_steps, float guidance, int solver,
                          foley_progress_fn progress, void* user, cudaStream_t st);
     foley_status dac_finalize();
     foley_status dac_decode(const float* z, int batch, int L, float* wav, cudaStream_t st);

@@ -391,6 +391,78 @@ __global__ void cfg_euler_kernel(const __nv_bfloat16* y, float* lat, __nv_bfloat
     }
 }
 
+// Multi-stage flow-matching solvers (heun-2 / midpoint-2 / kutta-4; scheduling_flow_match_discrete.py:299-373) inside the
+// engine loop: same CFG combine as cfg_euler_kernel, then one stage of the reference scheduler's state machine.  The
+// host precomputes one SolverCall per model call (the reference feeds consecutive `timesteps` entries to the model while
+// `step_index` only advances after the last stage — mirrored by the table, not "fixed"); the kernel reads the entry of
+// the current call through the device step counter, so the captured graph is the same for every call.
+struct SolverCall {
+    float dt;            // step size of this stage (dt, or dt/2)
+    float c0, c1, c2, cm; // kind 2: derivative = ((c0*d0 + c1*d1) + c2*d2) + cm*mo, every product and sum rounded (torch eager)
+    int kind;            // 0: derivative = model output; 1: 0.5*(d0 + mo) (heun last stage); 2: kutta last stage
+    int store_slot;      // >= 0: keep the model output as derivative d[store_slot]
+    int save_sample;     // 1: keep the incoming latents as the step's base sample
+    int base_saved;      // 1: update from the saved base sample instead of the incoming latents
+};
+__global__ void cfg_solver_kernel(const __nv_bfloat16* y, float* lat, __nv_bfloat16* x_next, float* d0, float* d1,
+                                  float* d2, float* samp0, int B, int n_cond, int ch, int L, float guidance,
+                                  const SolverCall* table, const int* step_ptr) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+    const SolverCall sc = table[*step_ptr];
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int l = l0 + i, c = c0 + threadIdx.x;
+        float v = 0.f;
+        if (l < L && c < ch) {
+            if (n_cond == 2) {
+                const float u = __bfloat162float(y[(static_cast<long long>(b) * L + l) * ch + c]);
+                const float t = __bfloat162float(y[(static_cast<long long>(B + b) * L + l) * ch + c]);
+                v = bf16_round(u + bf16_round(guidance * bf16_round(t - u)));
+            } else {
+                v = __bfloat162float(y[(static_cast<long long>(b) * L + l) * ch + c]);
+            }
+        }
+        tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, l = l0 + threadIdx.x;
+        if (c < ch && l < L) {
+            const long long o = (static_cast<long long>(b) * ch + c) * L + l;
+            const float mo = tile[threadIdx.x][i];
+            const float cur = lat[o];
+            if (sc.save_sample) samp0[o] = cur;
+            if (sc.store_slot == 0) d0[o] = mo;
+            else if (sc.store_slot == 1) d1[o] = mo;
+            else if (sc.store_slot == 2) d2[o] = mo;
+            float der = mo;
+            if (sc.kind == 1) {
+                der = __fmul_rn(0.5f, __fadd_rn(d0[o], mo));
+            } else if (sc.kind == 2) {
+                float a = __fmul_rn(sc.c0, d0[o]);
+                a = __fadd_rn(a, __fmul_rn(sc.c1, d1[o]));
+                a = __fadd_rn(a, __fmul_rn(sc.c2, d2[o]));
+                der = __fadd_rn(a, __fmul_rn(sc.cm, mo));
+            }
+            const float base = sc.base_saved ? samp0[o] : cur;
+            const float nv = __fadd_rn(base, __fmul_rn(der, sc.dt));
+            lat[o] = nv;
+            tile[threadIdx.x][i] = nv;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int l = l0 + i, c = c0 + threadIdx.x;
+        if (l < L && c < ch) {
+            const __nv_bfloat16 v = __float2bfloat16_rn(tile[i][threadIdx.x]);
+            for (int r = 0; r < n_cond; ++r)
+                x_next[((static_cast<long long>(r) * B + b) * L + l) * ch + c] = v;
+        }
+    }
+}
+
 // Advances the device-side step counter and the per-group timestep rows (one tiny launch per step so the
 // whole step can be replayed as one CUDA graph).
 __global__ void advance_step_kernel(int* step_ptr, int* trow_of_grp, int G) {

@@ -52,6 +52,8 @@ def load_library(path=None):
     lib.foley_dit_forward.argtypes = [c_void_p, c_void_p, POINTER(c_float), c_int32, c_void_p, c_void_p]
     lib.foley_denoise.argtypes = [c_void_p, c_void_p, POINTER(c_float), c_int32, c_float, PROGRESS_FN, c_void_p,
                                   c_void_p]
+    lib.foley_denoise_solver.argtypes = [c_void_p, c_void_p, POINTER(c_float), c_int32, c_float, c_int32, PROGRESS_FN,
+                                         c_void_p, c_void_p]
     lib.foley_dac_decode.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
     lib.foley_launch_count.argtypes = [c_void_p]
     lib.foley_launch_count.restype = c_int64
@@ -172,7 +174,16 @@ class FoleyEngine:
                                           _stream_ptr(self.device)))
         return out
 
-    def denoise(self, latents, sigmas, guidance, progress=None):
+    SOLVERS = {"euler": 0, "heun-2": 1, "midpoint-2": 2, "kutta-4": 3}    # FOLEY_SOLVER_*
+
+    def denoise_solver(self, latents, sigmas, guidance, solver, progress=None):
+        """The reference loop with any of its four solvers (name or FOLEY_SOLVER_* id), whole loop in the engine."""
+        sid = self.SOLVERS.get(solver, solver)
+        if sid not in (0, 1, 2, 3):
+            raise ValueError(f"Solver {solver} not supported. Supported solvers: {list(self.SOLVERS)}")
+        return self.denoise(latents, sigmas, guidance, progress=progress, solver_id=int(sid))
+
+    def denoise(self, latents, sigmas, guidance, progress=None, solver_id=0):
         """Euler loop in place on a copy of `latents` [B, latent, L]; returns fp32 latents on device."""
         p = self.plan
         if p is None:
@@ -183,8 +194,12 @@ class FoleyEngine:
         sig = torch.as_tensor(sigmas, dtype=torch.float32).flatten().cpu()
         arr = (c_float * sig.numel())(*sig.tolist())
         cb = PROGRESS_FN(lambda step, _u: progress(step)) if progress is not None else PROGRESS_FN()
-        _check(self.lib.foley_denoise(self._h, c_void_p(lat.data_ptr()), arr, sig.numel() - 1, float(guidance), cb,
-                                      None, _stream_ptr(self.device)))
+        if solver_id == 0:
+            _check(self.lib.foley_denoise(self._h, c_void_p(lat.data_ptr()), arr, sig.numel() - 1, float(guidance), cb,
+                                          None, _stream_ptr(self.device)))
+        else:
+            _check(self.lib.foley_denoise_solver(self._h, c_void_p(lat.data_ptr()), arr, sig.numel() - 1,
+                                                 float(guidance), solver_id, cb, None, _stream_ptr(self.device)))
         return lat
 
     def dac_decode(self, z):

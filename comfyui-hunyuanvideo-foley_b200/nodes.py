@@ -129,7 +129,8 @@ class FoleyDAC:
         return cls(engine)
 
     def decode(self, z):
-        return self.engine.dac_decode(z)
+        from . import torch_ops as ops
+        return ops.dac_decode(self.engine, z.to(self.engine.device))
 
     def to(self, *args, **kwargs):
         return self

@@ -164,15 +164,18 @@ def denoise_process_with_generator(visual_feats, text_feats, audio_len_in_s, mod
         clip, sync, text = torch.cat([uclip, clip]), torch.cat([usync, sync]), torch.cat([utext, text])
 
     # the engine shares the (identical, `.repeat`-ed in the reference) condition rows between variations
-    engine.set_conditions(clip, sync, text, L=L, batch=local_batch)
+    from . import torch_ops as ops   # registers torch.ops.foley_b200.* (the C ABI surfaced as torch ops)
+    ops.set_conditions(engine, clip, sync, text, L, local_batch)
     pbar = ProgressBar(num_inference_steps)
     progress = (lambda step: pbar.update(1)) if model_dict.get("report_progress", True) else None
     with torch.inference_mode():
-        if sampler == "euler":     # the benchmarked solver: whole loop inside the engine, one CUDA graph per step
-            latents = engine.denoise(latents.to(device), sigmas, guidance_scale, progress=progress)
-        else:
+        if model_dict.get("host_solver", False) and sampler != "euler":
+            # the reference scheduler's stage machine on the host around foley_dit_forward (cross-check path)
             latents = _denoise_multistage(engine, latents.to(device), sigmas, guidance_scale, sampler,
                                           2 if guidance_scale > 1.0 else 1, progress)
+        else:   # whole loop inside the engine, one CUDA graph replayed per model call, for all four solvers
+            latents = ops.denoise(engine, latents.to(device, torch.float32), sigmas, guidance_scale, solver=sampler,
+                                  progress=progress)
         if not decode:
             return latents, model_dict.dac_model.sample_rate if "dac_model" in model_dict else 48000
         audio = model_dict.dac_model.decode(latents)

@@ -107,6 +107,17 @@ typedef void (*foley_progress_fn)(int32_t step, void* user);
 foley_status foley_denoise(foley_engine* e, float* latents, const float* sigmas, int32_t n_steps,
                            float guidance, foley_progress_fn progress, void* user, void* stream);
 
+/* ---- the same loop with the reference scheduler's other solvers (scheduling_flow_match_discrete.py:299-373) ---
+ * solver: FOLEY_SOLVER_*; EULER is identical to foley_denoise.  n_calls model evaluations are made, call i with
+ * timestep sigmas[i]*1000 exactly as the reference's loop does (utils.py:215-246): the scheduler treats consecutive
+ * calls as inner stages of one step and only advances sigma -> sigma_next after a solver's last stage, so
+ * heun-2 / midpoint-2 cover n_calls/2 sigma intervals and kutta-4 n_calls/4.  That behaviour is reproduced, not
+ * corrected.  sigmas: n_calls+1 host floats. */
+enum { FOLEY_SOLVER_EULER = 0, FOLEY_SOLVER_HEUN2 = 1, FOLEY_SOLVER_MIDPOINT2 = 2, FOLEY_SOLVER_KUTTA4 = 3 };
+foley_status foley_denoise_solver(foley_engine* e, float* latents, const float* sigmas, int32_t n_calls,
+                                  float guidance, int32_t solver, foley_progress_fn progress, void* user,
+                                  void* stream);
+
 /* ---- DAC-VAE decode (dac.py:280-303) ----------------------------------------------------------
  * z: [batch, latent_dim, L] f32 -> wav: [batch, 1, L*hop] f32 (hop = 960). */
 foley_status foley_dac_decode(foley_engine* e, const float* z, int32_t batch, int32_t L, float* wav,

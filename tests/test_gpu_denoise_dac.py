@@ -152,3 +152,62 @@ def test_multistage_solvers_match_reference(golden_dir, tag):
     r16, r32 = rel_l2(lat.cpu(), want16), rel_l2(lat.cpu(), gold["latents"])
     print(f"\n[{tag}] engine vs oracle(cuda_bf16) {r16:.3e} | vs reference fp32 {r32:.3e} | oracle gap {gap:.3e}")
     assert r16 <= 1.5 * gap + 1e-3 and r32 <= 1.5 * gap + 1e-3
+    # The loop above ran inside the engine (foley_denoise_solver: one graph per model call, stage table on the device).
+    # The reference scheduler's stage machine on the host around foley_dit_forward must give the same bits.
+    md_host = cfgmod.AttributeDict({"foley_model": model, "device": torch.device("cuda", 0), "host_solver": True})
+    gen = torch.Generator(device="cpu").manual_seed(123)
+    lat_host, _ = sampling.denoise_process_with_generator(visual, text, a["duration"], md_host, cfg, a["guidance"],
+                                                          a["steps"], a["batch"], a["sampler"], generator=gen,
+                                                          decode=False)
+    assert torch.equal(lat.cpu(), lat_host.cpu())
+    assert eng.debug_flags()[0] == 0
+
+
+@pytest.mark.parametrize("solver", ["heun-2", "midpoint-2", "kutta-4"])
+@pytest.mark.parametrize("n_calls,guidance,graph", [(7, 4.5, 1), (5, 1.0, 0)])
+def test_engine_solver_ragged_call_counts(solver, n_calls, guidance, graph):
+    """Call counts that stop in the middle of a solver's stage group (the reference loop allows any `steps`), with and
+    without CFG / CUDA graph: foley_denoise_solver == host stage machine, bit for bit; and the torch op surface."""
+    sampling, ops = load_pkg("sampling"), load_pkg("torch_ops")
+    eng, c, sd = make_engine("tiny")
+    eng.set_option("cuda_graph", graph)
+    feats, L, Lv, S = _feats(c, sd, 1.0, True)
+    clip, sync, text = O.build_cfg_batch(sd, feats, 1, guidance)
+    ops.set_conditions(eng, clip.cuda(), sync.cuda(), text.cuda(), L, 2)
+    noise = torch.randn((2, 128, L), generator=torch.Generator().manual_seed(11))
+    sig = sampling.sigma_schedule(n_calls)
+    seen = []
+    got = ops.denoise(eng, noise.cuda(), sig, guidance, solver=solver, progress=seen.append)
+    assert seen == list(range(1, n_calls + 1))
+    want = sampling._denoise_multistage(eng, noise.cuda(), sig, guidance, solver, clip.shape[0], None)
+    assert torch.equal(got.cpu(), want.cpu())
+    # euler through the generic entry point == foley_denoise
+    e1 = eng.denoise_solver(noise.cuda(), sig, guidance, "euler")
+    e2 = eng.denoise(noise.cuda(), sig, guidance)
+    assert torch.equal(e1, e2)
+    with pytest.raises(ValueError):
+        eng.denoise_solver(noise.cuda(), sig, guidance, "dpm++")
+    assert eng.debug_flags()[0] == 0
+
+
+def test_torch_ops_surface():
+    """torch.ops.foley_b200.* call the same C-ABI entry points as the ctypes binding; CPU tensors are refused."""
+    ops = load_pkg("torch_ops")
+    E = load_pkg("engine")
+    eng, c, sd = make_engine("tiny")
+    h = ops.register_engine(eng)
+    assert ops.register_engine(eng) == h
+    feats, L, Lv, S = _feats(c, sd, 1.0, True)
+    clip, sync, text = O.build_cfg_batch(sd, feats, 1, 4.5)
+    torch.ops.foley_b200.set_conditions(h, clip.cuda(), sync.cuda(), text.cuda(), L, 1)
+    x = torch.randn(2, 128, L, generator=torch.Generator().manual_seed(3)).cuda()
+    t = torch.tensor([500.0])
+    y_op = torch.ops.foley_b200.dit_forward(h, x, t)
+    assert torch.equal(y_op, eng.dit_forward(x, 500.0))
+    sig = O.sigma_schedule(3)
+    lat_op = torch.ops.foley_b200.denoise(h, x[:1], sig, 4.5)
+    assert torch.equal(lat_op, eng.denoise(x[:1], sig, 4.5))
+    with pytest.raises(E.FoleyError):
+        torch.ops.foley_b200.dit_forward(h, x.cpu(), t)
+    with pytest.raises(E.FoleyError):
+        torch.ops.foley_b200.dit_forward(h + 1000, x, t)

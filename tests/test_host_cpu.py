@@ -230,3 +230,39 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["value"] > 0 and "workload" in line["config"]
+
+
+def test_torch_ops_are_registered_and_refuse_cpu_tensors():
+    """torch.ops.foley_b200.* (the C ABI surfaced as torch ops): schemas exist, the CPU key raises instead of falling
+    back, the Meta key gives shapes."""
+    ops = load_pkg("torch_ops")
+    E = load_pkg("engine")
+    for name in ("set_conditions", "dit_forward", "denoise", "denoise_solver", "dac_decode"):
+        assert hasattr(torch.ops.foley_b200, name)
+    x = torch.zeros(2, 128, 10)
+    with pytest.raises(E.FoleyError):
+        torch.ops.foley_b200.dit_forward(1, x, torch.tensor([1.0]))
+    with pytest.raises(E.FoleyError):
+        torch.ops.foley_b200.denoise_solver(1, x, torch.linspace(1, 0, 5), 4.5, 3)
+    assert torch.ops.foley_b200.dac_decode(1, x.to("meta")).shape == (2, 1, 9600)
+    assert torch.ops.foley_b200.denoise(1, x.to("meta"), torch.linspace(1, 0, 5).to("meta"), 4.5).shape == x.shape
+    with pytest.raises(ValueError):
+        ops.denoise(object.__new__(E.FoleyEngine), x, torch.linspace(1, 0, 5), 4.5, solver="dpm++")
+    assert ops.SOLVER_IDS == E.FoleyEngine.SOLVERS
+
+
+def test_solver_stage_machine_matches_reference_scheduler_rules():
+    """The host stage machine used as the cross-check of foley_denoise_solver: with a constant derivative field every
+    solver must land on sample + v * (sigma_k - sigma_0) after a whole number of stage groups, and the stage count per
+    sigma interval is 1 / 2 / 2 / 4 (scheduling_flow_match_discrete.py:299-373)."""
+    sampling = load_pkg("sampling")
+    sig = sampling.sigma_schedule(8)
+    v = torch.full((1, 4, 3), 2.0)
+    for solver, stages in sampling.FlowMatchSolverState.STAGES.items():
+        st = sampling.FlowMatchSolverState(solver, sig)
+        x = torch.zeros(1, 4, 3)
+        for _ in range(8):
+            x = st.step(v, x)
+        assert st.step_index == 8 // stages
+        want = 2.0 * float(sig[8 // stages] - sig[0])
+        assert torch.allclose(x, torch.full_like(x, want), atol=1e-6), solver
