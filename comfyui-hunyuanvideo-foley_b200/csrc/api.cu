@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "engine.cuh"
 #include "gemm_host.cuh"
+#include "safetensors.cuh"
 
 namespace foley {
 std::string& last_error_ref() {
@@ -85,6 +86,42 @@ extern "C" foley_status foley_engine_load_tensor(foley_engine* e, const char* na
     API_GUARD_END
 }
 
+extern "C" foley_status foley_engine_load_safetensors(foley_engine* e, const char* path, const char* prefix,
+                                                      int64_t* n_loaded) {
+    if (!e) return fail(FOLEY_ERR_INVALID, "null engine");
+    API_GUARD_BEGIN
+    return e->impl.load_safetensors(path, prefix, n_loaded);
+    API_GUARD_END
+}
+
+// Header-only inspection (no CUDA): tensor count, payload bytes, element counts per floating dtype.
+extern "C" foley_status foley_safetensors_probe(const char* path, int64_t* n_tensors, int64_t* data_bytes,
+                                                int64_t numel_by_dtype[5]) {
+    if (!path) return fail(FOLEY_ERR_INVALID, "foley_safetensors_probe: null path");
+    API_GUARD_BEGIN
+    StFile f;
+    std::string err;
+    if (!f.open_file(path, &err)) return fail(FOLEY_ERR_INVALID, err);
+    if (n_tensors) *n_tensors = static_cast<int64_t>(f.entries.size());
+    if (data_bytes) *data_bytes = static_cast<int64_t>(f.data_bytes);
+    if (numel_by_dtype) {
+        for (int i = 0; i < 5; ++i) numel_by_dtype[i] = 0;
+        for (const StEntry& en : f.entries) {
+            const int dt = st_dtype_to_foley(en.dtype);
+            if (dt < 0) continue;
+            int64_t numel = 1;
+            for (int64_t d : en.shape) numel *= d;
+            numel_by_dtype[dt] += numel;
+        }
+    }
+    return FOLEY_OK;
+    API_GUARD_END
+}
+
+extern "C" int32_t foley_fp8_wraps(const char* tensor_name, int32_t ndim) {
+    return tensor_name && fp8_wraps(tensor_name, ndim) ? 1 : 0;
+}
+
 extern "C" foley_status foley_engine_finalize(foley_engine* e) {
     if (!e) return fail(FOLEY_ERR_INVALID, "null engine");
     API_GUARD_BEGIN
@@ -159,6 +196,9 @@ extern "C" foley_status foley_engine_set_option(foley_engine* e, const char* key
         if (e->impl.plan.valid && value > e->impl.max_splits) return fail(FOLEY_ERR_STATE, "raise max_splits before set_conditions");
         e->impl.max_splits_used = static_cast<int>(value);
         e->impl.graph_valid = false;
+    } else if (k == "fp8_weight_storage") {
+        if (value < 0 || value > 2) return fail(FOLEY_ERR_INVALID, "fp8_weight_storage must be 0 (none), 1 (e4m3fn) or 2 (e5m2)");
+        e->impl.fp8_storage = static_cast<int>(value);
     } else return fail(FOLEY_ERR_INVALID, "unknown option " + k);
     return FOLEY_OK;
 }

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "attention.cuh"
+#include "safetensors.cuh"
 
 namespace foley {
 
@@ -97,8 +98,8 @@ static bool name_is_used(const std::string& n) {
 
 foley_status Engine::load_tensor(const char* name, const void* data, const int64_t* shape, int ndim, int dtype) {
     if (!name || !data || ndim < 0 || ndim > 4) return fail(FOLEY_ERR_INVALID, "load_tensor: bad arguments");
-    if (dtype != FOLEY_DT_BF16 && dtype != FOLEY_DT_F32 && dtype != FOLEY_DT_F16)
-        return fail(FOLEY_ERR_INVALID, "load_tensor: dtype must be bf16, f32 or f16");
+    if (dtype < FOLEY_DT_BF16 || dtype > FOLEY_DT_F8_E5M2)
+        return fail(FOLEY_ERR_INVALID, "load_tensor: dtype must be bf16, f32, f16, f8_e4m3fn or f8_e5m2");
     const std::string n(name);
     if (!name_is_used(n)) return FOLEY_OK;
     FOLEY_CUDA_OK(cudaSetDevice(device));
@@ -106,7 +107,8 @@ foley_status Engine::load_tensor(const char* name, const void* data, const int64
     rt.dtype = dtype;
     rt.numel = 1;
     for (int i = 0; i < ndim; ++i) { rt.shape.push_back(shape[i]); rt.numel *= shape[i]; }
-    const size_t bytes = static_cast<size_t>(rt.numel) * (dtype == FOLEY_DT_F32 ? 4 : 2);
+    rt.fp8_mode = fp8_wraps(n, ndim) ? fp8_storage : 0;   // reference quantization != none (utils.py:410-485)
+    const size_t bytes = static_cast<size_t>(rt.numel) * (dtype == FOLEY_DT_F32 ? 4 : dtype >= FOLEY_DT_F8_E4M3FN ? 1 : 2);
     FOLEY_CUDA_OK(cudaMalloc(&rt.dev, std::max<size_t>(bytes, 16)));
     FOLEY_CUDA_OK(cudaMemcpy(rt.dev, data, bytes, cudaMemcpyDefault));  // host or device source
     auto it = raw.find(n);
@@ -116,13 +118,39 @@ foley_status Engine::load_tensor(const char* name, const void* data, const int64
     return FOLEY_OK;
 }
 
+// The whole checkpoint in one call: map the file, parse the header, copy every tensor the path uses from the mapping
+// to the device (nodes.py:85-104 without the meta-init / to_empty / load_state_dict / .to(dtype) passes over host RAM).
+foley_status Engine::load_safetensors(const char* path, const char* prefix, int64_t* n_loaded) {
+    if (!path) return fail(FOLEY_ERR_INVALID, "load_safetensors: null path");
+    StFile f;
+    std::string err;
+    if (!f.open_file(path, &err)) return fail(FOLEY_ERR_INVALID, err);
+    const std::string pre(prefix ? prefix : "");
+    int64_t count = 0;
+    for (const StEntry& e : f.entries) {
+        const std::string name = pre + e.name;
+        if (!name_is_used(name)) continue;
+        const int dt = st_dtype_to_foley(e.dtype);
+        if (dt < 0) {
+            // integer / f64 tensors: only acceptable for entries the path does not read (e.g. step counters)
+            if (name.find("num_batches_tracked") != std::string::npos) continue;
+            return fail(FOLEY_ERR_UNSUPPORTED, "load_safetensors: dtype " + e.dtype + " of " + e.name + " is not supported");
+        }
+        if (e.shape.size() > 4) return fail(FOLEY_ERR_INVALID, "load_safetensors: rank > 4: " + e.name);
+        ST_OK(load_tensor(name.c_str(), f.data + e.begin, e.shape.data(), static_cast<int>(e.shape.size()), dt));
+        ++count;
+    }
+    if (n_loaded) *n_loaded = count;
+    return FOLEY_OK;
+}
+
 foley_status Engine::raw_as_bf16(const std::string& name, bf16** out, RawTensor** rtp) {
     auto it = raw.find(name);
     if (it == raw.end()) return fail(FOLEY_ERR_MISSING, "missing tensor: " + name);
     RawTensor& rt = it->second;
     bf16* d = nullptr;
     FOLEY_CUDA_OK(cudaMalloc(&d, std::max<size_t>(rt.numel * 2, 16)));
-    convert_to_bf16_kernel<<<blocks_for(rt.numel, 256), 256>>>(rt.dev, rt.dtype, rt.numel, d);
+    convert_to_bf16_kernel<<<blocks_for(rt.numel, 256), 256>>>(rt.dev, rt.dtype, rt.numel, d, rt.fp8_mode);
     FOLEY_CUDA_OK(cudaGetLastError());
     *out = d;
     if (rtp) *rtp = &rt;
@@ -172,7 +200,7 @@ static foley_status take_pair(Engine* e, const std::string& n1, const std::strin
         *K = static_cast<int>(rt.shape[1]);
         *taps = rt.shape.size() == 3 ? static_cast<int>(rt.shape[2]) : 1;
         FOLEY_CUDA_OK(cudaMalloc(w, rt.numel * 2));
-        convert_to_bf16_kernel<<<blocks_for(rt.numel, 256), 256>>>(rt.dev, rt.dtype, rt.numel, *w);
+        convert_to_bf16_kernel<<<blocks_for(rt.numel, 256), 256>>>(rt.dev, rt.dtype, rt.numel, *w, rt.fp8_mode);
         FOLEY_CUDA_OK(cudaGetLastError());
         return FOLEY_OK;
     };
@@ -496,7 +524,7 @@ foley_status Engine::set_conditions(const void* clip, const void* sync, const vo
     int* idx_dev = sc_idx;
     const size_t US = static_cast<size_t>(U) * S, UT = static_cast<size_t>(U) * T, ULv = static_cast<size_t>(U) * Lv;
     auto to_bf16 = [&](const void* src, bf16* dst, long long n) -> foley_status {
-        convert_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, dtype, n, dst);
+        convert_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, dtype, n, dst, 0);
         FOLEY_CUDA_OK(cudaGetLastError());
         ++launches;
         return FOLEY_OK;

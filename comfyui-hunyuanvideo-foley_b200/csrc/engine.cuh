@@ -21,6 +21,7 @@ struct RawTensor {
     std::vector<int64_t> shape;
     int dtype = FOLEY_DT_BF16;
     int64_t numel = 0;
+    int fp8_mode = 0;             // round through this FP8 format at repack (0 none, 1 e4m3fn, 2 e5m2)
 };
 
 struct LinearW {                  // K-major weight [N, Ktot] + optional bias [N]
@@ -56,6 +57,7 @@ class Engine {
     int C = 0, H = 0, NT = 0, NS = 0, F = 0, Hs = 0, Hy = 0, LAT = 0;
     int64_t launches = 0;
     bool finalized = false;
+    int fp8_storage = 0;          // option "fp8_weight_storage": the reference's quantization != none for tensors loaded next
     std::unordered_map<std::string, RawTensor> raw;
 
     // ---- DiT weights
@@ -123,6 +125,7 @@ class Engine {
     ~Engine();
     foley_status create(const foley_config* c, int dev);
     foley_status load_tensor(const char* name, const void* data, const int64_t* shape, int ndim, int dtype);
+    foley_status load_safetensors(const char* path, const char* prefix, int64_t* n_loaded);
     foley_status finalize();
     foley_status set_conditions(const void* clip, const void* sync, const void* text, int dtype, int U, int Lv,
                                 int S, int T, int L, int B, cudaStream_t st);

@@ -476,23 +476,46 @@ __global__ void advance_step_kernel(int* step_ptr, int* trow_of_grp, int G) {
 }
 
 // ------------------------------------------------------------------------------------------------ weight repack
-__global__ void convert_to_bf16_kernel(const void* src, int src_dtype, long long n, __nv_bfloat16* dst) {
+// ---- source dtypes of checkpoints: bf16 / f32 / f16 and the two FP8 storage formats (FOLEY_DT_*)
+__device__ __forceinline__ float decode_f8_e4m3fn(uint8_t b) {   // 1-4-3, bias 7, no inf, NaN = S.1111.111
+    const uint32_t sign = (b & 0x80u) << 24, e = (b >> 3) & 0xFu, m = b & 0x7u;
+    if (e == 0xFu && m == 0x7u) return __uint_as_float(sign | 0x7FC00000u);
+    if (e == 0) return __uint_as_float(sign | __float_as_uint(static_cast<float>(m) * 0.001953125f));   // m * 2^-9
+    return __uint_as_float(sign | ((e + 120u) << 23) | (m << 20));
+}
+__device__ __forceinline__ float decode_f8_e5m2(uint8_t b) {     // the top byte of an fp16
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(b) << 8));
+}
+__device__ __forceinline__ float load_any_as_float(const void* src, int src_dtype, long long i) {
+    switch (src_dtype) {
+        case 0: return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
+        case 1: return reinterpret_cast<const float*>(src)[i];
+        case 2: return __half2float(reinterpret_cast<const __half*>(src)[i]);
+        case 3: return decode_f8_e4m3fn(reinterpret_cast<const uint8_t*>(src)[i]);
+        default: return decode_f8_e5m2(reinterpret_cast<const uint8_t*>(src)[i]);
+    }
+}
+// Round-to-nearest-even through an FP8 storage format (what `weight.to(torch.float8_*)` followed by the per-forward
+// upcast does in the reference's FP8WeightWrapper, utils.py:316-356).  mode: 1 = e4m3fn, 2 = e5m2.  Overflow -> NaN
+// (e4m3fn) / inf (e5m2), like torch's casts; weights never get there.
+__device__ __forceinline__ float round_through_fp8(float v, int mode) {
+    if (mode == 1) return decode_f8_e4m3fn(static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_NOSAT, __NV_E4M3)));
+    if (mode == 2) return decode_f8_e5m2(static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_NOSAT, __NV_E5M2)));
+    return v;
+}
+// fp8_mode != 0: the value is first rounded to bf16 (load_state_dict into bf16 parameters), then stored in FP8; a
+// checkpoint tensor that already is in that FP8 format passes through unchanged.
+__global__ void convert_to_bf16_kernel(const void* src, int src_dtype, long long n, __nv_bfloat16* dst, int fp8_mode) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float v;
-    if (src_dtype == 0) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
-    else if (src_dtype == 1) v = reinterpret_cast<const float*>(src)[i];
-    else v = __half2float(reinterpret_cast<const __half*>(src)[i]);
+    float v = bf16_round(load_any_as_float(src, src_dtype, i));
+    if (fp8_mode != 0 && src_dtype != fp8_mode + 2) v = round_through_fp8(v, fp8_mode);
     dst[i] = __float2bfloat16_rn(v);
 }
 __global__ void convert_to_f32_kernel(const void* src, int src_dtype, long long n, float* dst) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float v;
-    if (src_dtype == 0) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
-    else if (src_dtype == 1) v = reinterpret_cast<const float*>(src)[i];
-    else v = __half2float(reinterpret_cast<const __half*>(src)[i]);
-    dst[i] = v;
+    dst[i] = load_any_as_float(src, src_dtype, i);
 }
 
 // Conv weight [N, K, taps] -> tap-major GEMM rows dst[(n*row_mul + row_add) , tap*K + k]; also used for plain

@@ -11,7 +11,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfoley_b200.so")
 
-FOLEY_DT = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}
+FOLEY_DT = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2, torch.float8_e4m3fn: 3, torch.float8_e5m2: 4}
+FP8_STORAGE = {"none": 0, None: 0, "fp8_e4m3fn": 1, "fp8_e5m2": 2}   # option "fp8_weight_storage"
 
 
 class FoleyError(RuntimeError):
@@ -46,6 +47,10 @@ def load_library(path=None):
     lib.foley_engine_destroy.argtypes = [c_void_p]
     lib.foley_engine_destroy.restype = None
     lib.foley_engine_load_tensor.argtypes = [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int32, c_int32]
+    lib.foley_engine_load_safetensors.argtypes = [c_void_p, c_char_p, c_char_p, POINTER(c_int64)]
+    lib.foley_safetensors_probe.argtypes = [c_char_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]
+    lib.foley_fp8_wraps.argtypes = [c_char_p, c_int32]
+    lib.foley_fp8_wraps.restype = c_int32
     lib.foley_engine_finalize.argtypes = [c_void_p]
     lib.foley_set_conditions.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_int32, c_void_p]
@@ -122,11 +127,25 @@ class FoleyEngine:
             pass
 
     # ---- weights
+    def set_fp8_weight_storage(self, quantization):
+        """The reference's `quantization` choice ("none" / "fp8_e4m3fn" / "fp8_e5m2", nodes.py:66,106-121) for the
+        tensors loaded next: the weights it would keep in FP8 are rounded through that format on the device."""
+        if quantization not in FP8_STORAGE:
+            raise ValueError(f"unknown quantization {quantization!r}")
+        self.set_option("fp8_weight_storage", FP8_STORAGE[quantization])
+
+    def load_safetensors(self, path, prefix=""):
+        """The whole .safetensors checkpoint, file -> device, no host state dict (foley_engine_load_safetensors)."""
+        n = c_int64()
+        _check(self.lib.foley_engine_load_safetensors(self._h, os.fsencode(path), prefix.encode(), ctypes.byref(n)))
+        self._finalized = False
+        return n.value
+
     def load_tensor(self, name, t):
         t = t.detach()
         if t.dtype not in FOLEY_DT:
             t = t.float()
-        t = t.contiguous()
+        t = t.contiguous()   # fp8 checkpoint tensors travel as their bytes and are de-quantised on the device
         shape = (c_int64 * max(t.dim(), 1))(*t.shape)
         _check(self.lib.foley_engine_load_tensor(self._h, name.encode(), c_void_p(t.data_ptr()), shape, t.dim(),
                                                  FOLEY_DT[t.dtype]))
@@ -148,7 +167,7 @@ class FoleyEngine:
         if not self._finalized:
             self.finalize()
         U = clip.shape[0]
-        dt = clip.dtype if clip.dtype in FOLEY_DT else torch.float32
+        dt = clip.dtype if clip.dtype in (torch.bfloat16, torch.float32, torch.float16) else torch.float32
         clip, sync, text = (x.to(self.device, dt).contiguous() for x in (clip, sync, text))
         if sync.shape[0] != U or text.shape[0] != U:
             raise FoleyError("clip / sync / text must share the leading n_cond dimension")

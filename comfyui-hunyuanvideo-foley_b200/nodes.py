@@ -81,13 +81,40 @@ class FoleyModel:
         self.sync_len = kw.get("sync_length", 192)
 
     @classmethod
-    def from_state_dict(cls, state_dict, model_size=None, device=None, dtype=torch.bfloat16):
+    def from_state_dict(cls, state_dict, model_size=None, device=None, dtype=torch.bfloat16, quantization="none"):
+        """quantization: "none" or the FP8 storage mode the reference would wrap its Linear / Conv weights in
+        (checkpoint.resolve_quantization); the engine rounds those weights through it and keeps computing in bf16."""
         model_size = model_size or detect_model_size(state_dict)
         cfg = load_model_config(model_size)
         engine = FoleyEngine(dict(cfg.model_config.model_kwargs), device=device, with_dac=False)
+        engine.set_fp8_weight_storage(quantization)
         engine.load_state_dict(state_dict)
         engine.finalize()
         return cls(engine, state_dict["empty_clip_feat"], state_dict["empty_sync_feat"], cfg, dtype)
+
+    @classmethod
+    def from_safetensors(cls, path, precision="bf16", quantization="auto", device=None, cfg=None):
+        """The Model Loader's work (reference nodes.py:72-126) without a host state dict: header-only dtype sniffing
+        (utils.py:492-515), then file -> device through foley_engine_load_safetensors."""
+        from . import checkpoint as ck
+        header, data_start = ck.read_header(path)
+        dts = [(ck.ST_DTYPES.get(e["dtype"]), int(torch.tensor(e["shape"]).prod()) if e["shape"] else 1)
+               for e in header.values()]
+        dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}.get(precision, torch.bfloat16)
+        if precision == "auto":
+            dtype = ck.detect_major_precision(dts)
+            logger.info("Auto precision selected from checkpoint: %s", dtype)
+        qmode = ck.resolve_quantization(quantization, ck.detect_fp8(d for d, _ in dts))
+        w = header.get("audio_embedder.proj.weight")
+        model_size = "xl" if w is not None and int(w["shape"][0]) == 1408 else "xxl"
+        cfg = cfg if cfg is not None else load_model_config(model_size)
+        engine = FoleyEngine(dict(cfg.model_config.model_kwargs), device=device, with_dac=False)
+        engine.set_fp8_weight_storage(qmode)
+        n = engine.load_safetensors(path)
+        engine.finalize()
+        logger.info("Loaded %d tensors from %s straight into the B200 engine (fp8 storage emulation: %s)", n, path, qmode)
+        return cls(engine, ck.read_tensor(path, "empty_clip_feat", header, data_start),
+                   ck.read_tensor(path, "empty_sync_feat", header, data_start), cfg, dtype)
 
     def get_empty_clip_sequence(self, bs=None, len=None):      # hifi_foley.py:620-625
         len = len if len is not None else self.clip_len
@@ -149,7 +176,7 @@ class HunyuanModelLoader:
             "required": {
                 "model_name": (_foley_files(),),
                 "precision": (["auto", "bf16", "fp16", "fp32"], {"default": "bf16", "tooltip": "The B200 engine computes with bf16 tensor-core GEMMs and fp32 accumulation / residuals for every choice"}),
-                "quantization": (["none", "fp8_e4m3fn", "fp8_e5m2", "auto"], {"default": "auto", "tooltip": "Accepted for workflow compatibility; fp8 checkpoints are de-quantised to bf16 at load"}),
+                "quantization": (["none", "fp8_e4m3fn", "fp8_e5m2", "auto"], {"default": "auto", "tooltip": "Same numbers as the reference's FP8 weight-only storage (weights rounded through FP8 at load); the engine keeps them resident in bf16"}),
             },
         }
 
@@ -163,12 +190,22 @@ class HunyuanModelLoader:
         model_path = folder_paths.get_full_path("foley", model_name)
         if model_path is None or not os.path.exists(model_path):
             raise FileNotFoundError(f"Hunyuan-Foley checkpoint not found: {model_name}")
-        state_dict = load_torch_file(model_path, device=mm.unet_offload_device())
         if precision not in ("auto", "bf16"):
-            logger.warning("precision=%s requested; the B200 engine runs bf16 GEMMs with fp32 accumulation", precision)
-        model = FoleyModel.from_state_dict(state_dict, device=mm.get_torch_device())
+            logger.warning("precision=%s requested; the B200 engine runs bf16 GEMMs with fp32 accumulation "
+                           "(the choice still sets the dtype of the noise draw and features, as in the reference)", precision)
+        if str(model_path).endswith(".safetensors"):
+            model = FoleyModel.from_safetensors(model_path, precision, quantization, device=mm.get_torch_device())
+        else:   # .pt / .pth checkpoints go through a host state dict like the reference
+            from . import checkpoint as ck
+            state_dict = load_torch_file(model_path, device=mm.unet_offload_device())
+            tensors = [v for v in state_dict.values() if isinstance(v, torch.Tensor)]
+            dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}.get(precision, torch.bfloat16)
+            if precision == "auto":
+                dtype = ck.detect_major_precision((v.dtype, v.numel()) for v in tensors)
+            qmode = ck.resolve_quantization(quantization, ck.detect_fp8(v.dtype for v in tensors))
+            model = FoleyModel.from_state_dict(state_dict, device=mm.get_torch_device(), dtype=dtype, quantization=qmode)
+            del state_dict
         logger.info("Loaded HunyuanVideoFoley main model into the B200 engine: %s", model_name)
-        del state_dict
         return model
 
     def build_model(self, model_name, precision, quantization):

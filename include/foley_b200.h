@@ -33,7 +33,7 @@ enum {
     FOLEY_ERR_UNSUPPORTED = 5
 };
 
-enum { FOLEY_DT_BF16 = 0, FOLEY_DT_F32 = 1, FOLEY_DT_F16 = 2 };
+enum { FOLEY_DT_BF16 = 0, FOLEY_DT_F32 = 1, FOLEY_DT_F16 = 2, FOLEY_DT_F8_E4M3FN = 3, FOLEY_DT_F8_E5M2 = 4 };
 
 /* Hyper-parameters of configs/hunyuanvideo-foley-{xl,xxl}.yaml (model_config.model_kwargs) that the
  * hot path reads (hifi_foley.py:403-450), plus the torch semantics knobs the reference inherits. */
@@ -78,6 +78,20 @@ void         foley_engine_destroy(foley_engine* e);
  * (DAC encoder, final_layer.adaLN_modulation, ...) are accepted and ignored, like strict=False. */
 foley_status foley_engine_load_tensor(foley_engine* e, const char* name, const void* data,
                                       const int64_t* shape, int32_t ndim, int32_t dtype);
+/* The whole checkpoint in one call (nodes.py:85-104: load_torch_file -> init_empty_weights -> to_empty ->
+ * load_state_dict -> .to(dtype), and utils.py:61-87 for the DAC with prefix "dac."): `path` is a .safetensors file;
+ * it is mapped, its header parsed, and every tensor the hot path uses is copied from the mapping straight to the
+ * device under the name `prefix` + key.  FP8 checkpoints (utils.py:492-503) are de-quantised at finalize.  n_loaded
+ * (may be NULL) receives the number of tensors taken. */
+foley_status foley_engine_load_safetensors(foley_engine* e, const char* path, const char* prefix,
+                                           int64_t* n_loaded);
+/* Header-only inspection of a .safetensors file, no GPU needed: tensor count, payload bytes and element counts per
+ * FOLEY_DT_* (what _detect_ckpt_fp8 / _detect_ckpt_major_precision, utils.py:492-515, need). */
+foley_status foley_safetensors_probe(const char* path, int64_t* n_tensors, int64_t* data_bytes,
+                                     int64_t numel_by_dtype[5]);
+/* 1 if the reference's FP8 weight-only storage (quantization != "none", utils.py:410-485) replaces the module that
+ * owns this tensor — i.e. if option "fp8_weight_storage" rounds it through FP8 at load. */
+int32_t      foley_fp8_wraps(const char* tensor_name, int32_t ndim);
 /* Verifies that every tensor the hot path needs was provided; folds weight norm. */
 foley_status foley_engine_finalize(foley_engine* e);
 
@@ -132,7 +146,9 @@ foley_status foley_debug_read(foley_engine* e, const char* what, float* dst, int
 
 /* Reads and clears device debug words: out4[0] = code of the first pipeline wait that timed out (0 = none). */
 foley_status foley_debug_flags(uint32_t* out4);
-/* Runtime switches for tests / profiling: "cuda_graph" (0/1, default 1), "max_splits" (1..8, default 8). */
+/* Runtime switches: "cuda_graph" (0/1, default 1), "max_splits" (1..8, default 8), "fp8_weight_storage" (0 none /
+ * 1 e4m3fn / 2 e5m2; applies to tensors loaded AFTER the call: the Linear / Conv weights the reference would keep in
+ * FP8 are rounded through that format, so results match the reference's quantization setting; compute stays bf16). */
 foley_status foley_engine_set_option(foley_engine* e, const char* key, int64_t value);
 
 /* ---- low-level kernels exported for unit tests and micro-benchmarks --------------------------- */

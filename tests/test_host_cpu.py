@@ -266,3 +266,78 @@ def test_solver_stage_machine_matches_reference_scheduler_rules():
         assert st.step_index == 8 // stages
         want = 2.0 * float(sig[8 // stages] - sig[0])
         assert torch.allclose(x, torch.full_like(x, want), atol=1e-6), solver
+
+
+def test_fp8_wrap_rule_matches_what_the_reference_wraps(golden_dir=os.path.join(ROOT, "tests", "golden")):
+    """tests/golden/fp8_wrapped_tiny.json lists the modules the reference's _wrap_fp8_inplace replaced on its own tiny
+    model (all 56 Linear / Conv1d — its deny list never matches).  foley_fp8_wraps (C) and checkpoint.fp8_wraps (host
+    mirror) must select exactly those modules' weights from the state dict."""
+    from oracle import weights as W
+    E, ck = load_pkg("engine"), load_pkg("checkpoint")
+    lib = E.load_library()
+    gold = json.load(open(os.path.join(golden_dir, "fp8_wrapped_tiny.json")))
+    assert sorted(gold["wrapped"]) == sorted(gold["linear_like"])
+    sd = W.synth_dit_state_dict(W.model_config("tiny"), seed=0)
+    picked_c = sorted(k[:-len(".weight")] for k, v in sd.items() if lib.foley_fp8_wraps(k.encode(), v.dim()))
+    picked_py = sorted(k[:-len(".weight")] for k, v in sd.items() if ck.fp8_wraps(k, v.dim()))
+    assert picked_c == picked_py == sorted(gold["wrapped"])
+    assert not lib.foley_fp8_wraps(b"dac.decoder.model.0.weight", 3)
+    assert not lib.foley_fp8_wraps(b"triple_blocks.0.audio_self_q_norm.weight", 1)
+    assert not lib.foley_fp8_wraps(b"sync_pos_emb", 3)
+
+
+def test_loader_precision_and_quantization_resolution_match_reference():
+    """utils.py:492-515 and nodes.py:106-121."""
+    ck = load_pkg("checkpoint")
+    bf, f16, f32, e4, e5 = torch.bfloat16, torch.float16, torch.float32, torch.float8_e4m3fn, torch.float8_e5m2
+    assert ck.detect_fp8([bf, f32]) is None
+    assert ck.detect_fp8([bf, e5, e4]) == "fp8_e5m2" and ck.detect_fp8([e4, e5]) == "fp8_e4m3fn"
+    assert ck.detect_major_precision([(bf, 10), (f32, 11), (e4, 1000)]) == f32
+    assert ck.detect_major_precision([(e4, 5)]) == bf and ck.detect_major_precision([]) == bf
+    assert ck.detect_major_precision([(f16, 3), (bf, 3)]) == bf      # ties: first key of the reference's dict
+    assert ck.resolve_quantization("none", "fp8_e5m2") is None
+    assert ck.resolve_quantization("auto", None) == "fp8_e4m3fn"      # B200: capability 10 >= 9
+    assert ck.resolve_quantization("auto", "fp8_e5m2") == "fp8_e5m2"
+    assert ck.resolve_quantization("auto", None, capability_major=8) == "fp8_e5m2"
+    assert ck.resolve_quantization("fp8_e5m2", "fp8_e4m3fn") == "fp8_e5m2"
+    w = torch.tensor([0.3, -0.02, 1.7, 448.0, 0.0009765625 * 3])
+    assert torch.equal(ck.round_through_fp8(w, "fp8_e4m3fn").float(), w.bfloat16().to(e4).float())
+    assert torch.equal(ck.round_through_fp8(w.to(e5), "fp8_e5m2").float(), w.to(e5).float())
+
+
+def test_safetensors_probe_and_header_parser(tmp_path):
+    """foley_safetensors_probe parses the container without a GPU; the host writer/reader round-trips; malformed
+    files are refused with an error instead of a crash."""
+    E, ck = load_pkg("engine"), load_pkg("checkpoint")
+    lib = E.load_library()
+    g = torch.Generator().manual_seed(0)
+    tensors = {
+        "a.weight": torch.randn(8, 4, generator=g).bfloat16(),
+        'odd "name"\\x': torch.randn(3, generator=g),
+        "b.weight": torch.randn(2, 4, 3, generator=g).half(),
+        "q.weight": torch.randn(16, 8, generator=g).to(torch.float8_e4m3fn),
+        "r.weight": torch.randn(16, generator=g).to(torch.float8_e5m2),
+        "steps": torch.arange(3),
+        "empty": torch.zeros(0, 5),
+    }
+    path = str(tmp_path / "t.safetensors")
+    ck.write_safetensors(path, tensors, metadata={"format": "pt", "note": "x,{}[]"})
+    from safetensors.torch import load_file   # independent reader agrees with our writer
+    back = load_file(path)
+    assert set(back) == set(tensors) and all(torch.equal(back[k].view(torch.uint8), tensors[k].view(torch.uint8)) for k in tensors)
+    n, nbytes, by = ctypes.c_int64(), ctypes.c_int64(), (ctypes.c_int64 * 5)()
+    assert lib.foley_safetensors_probe(path.encode(), ctypes.byref(n), ctypes.byref(nbytes), by) == 0
+    assert n.value == len(tensors)
+    assert nbytes.value == sum(t.numel() * t.element_size() for t in tensors.values())
+    assert list(by) == [32, 3, 24, 128, 16]
+    hdr, start = ck.read_header(path)
+    assert torch.equal(ck.read_tensor(path, "b.weight", hdr, start), tensors["b.weight"])
+    # malformed: truncated payload, garbage header, header length beyond the file
+    raw = open(path, "rb").read()
+    bad = {"trunc": raw[:-5], "garbage": raw[:8] + b"not json" + raw[16:], "hlen": b"\xff" * 8 + raw[8:], "short": b"abc"}
+    for name, blob in bad.items():
+        p = str(tmp_path / f"{name}.safetensors")
+        open(p, "wb").write(blob)
+        assert lib.foley_safetensors_probe(p.encode(), None, None, None) == 1, name
+        assert b"safetensors" in lib.foley_last_error()
+    assert lib.foley_safetensors_probe(str(tmp_path / "missing.safetensors").encode(), None, None, None) == 1

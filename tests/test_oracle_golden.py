@@ -94,3 +94,29 @@ def test_interleaved_rope_positions_closed_form():
         assert torch.equal(v_pos, back_pos)
         assert torch.equal(back_tok, torch.arange(Lv))
         assert torch.equal(a_pos, 2 * torch.arange(L))
+
+
+def _fp8_storage_state_dict(sd, mode="fp8_e4m3fn"):
+    """What the reference loader leaves in the model with quantization != none (nodes.py:100-121): every parameter in
+    the compute dtype (bf16), Linear / Conv weights additionally rounded through the FP8 storage format."""
+    from conftest import load_pkg
+    ck = load_pkg("checkpoint")
+    out = {}
+    for k, v in sd.items():
+        v = v.to(torch.bfloat16)
+        out[k] = (ck.round_through_fp8(v, mode) if ck.fp8_wraps(k, v.dim()) else v).float()
+    return out
+
+
+def test_fp8_weight_storage_matches_reference_wrapper(golden_dir):
+    """Reference: bf16 model -> _wrap_fp8_inplace(e4m3fn) -> fp32 compute.  Oracle: the same forward on weights rounded
+    through FP8 by the rule checkpoint.fp8_wraps — pins both the rule (which modules) and the rounding."""
+    gold = torch.load(os.path.join(golden_dir, "dit_tiny_fp8e4m3_fp32.pt"))
+    c = W.model_config("tiny")
+    sd = _fp8_storage_state_dict(W.synth_dit_state_dict(c, seed=0))
+    sh = gold["shape"]
+    out = O.dit_forward(sd, c, *_dit_inputs(c, sh["B"], sh["L"], sh["Lv"], sh["S"]), policy="fp32")
+    assert rel_l2(out, gold["out"]) <= 1e-5
+    # and FP8 storage is not a no-op: the plain fp32 golden differs at the percent level
+    plain = torch.load(os.path.join(golden_dir, "dit_tiny_fp32.pt"))["out"]
+    assert rel_l2(gold["out"], plain) > 1e-3

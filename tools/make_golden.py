@@ -165,6 +165,27 @@ def gold_dac_full(ns):
     print("wrote", path, tuple(wav.shape), float(wav.abs().mean()))
 
 
+def gold_fp8_wrap(ns):
+    """The reference Model Loader's quantization path (nodes.py:106-121, utils.py:410-485) on the tiny config: which
+    modules _wrap_fp8_inplace really replaces, and the forward of the wrapped model (fp32 compute on CPU so that the
+    only difference to dit_tiny_fp32 is the FP8 storage of the weights)."""
+    import json
+    c = W.model_config("tiny")
+    model, _, sd = build_ref_model(ns, "tiny", torch.bfloat16)      # loader: params in the compute dtype ...
+    linear_like = [n for n, m in model.named_modules() if isinstance(m, (torch.nn.Linear, torch.nn.Conv1d, torch.nn.Conv2d))]
+    counts, _ = ns.utils._wrap_fp8_inplace(model, quantization="fp8_e4m3fn", state_dict=sd)   # ... then the FP8 wrap
+    wrapped = [n for n, m in model.named_modules() if type(m).__name__ == "FP8WeightWrapper"]
+    with open(os.path.join(GOLD, "fp8_wrapped_tiny.json"), "w") as f:
+        json.dump({"wrapped": wrapped, "linear_like": linear_like, "counts": counts}, f, indent=0)
+    model = model.float()
+    x, t, cond, clip, sync = dit_inputs(c, 2, 50, 8, 16)
+    with torch.inference_mode():
+        out = model(x=x, t=t, cond=cond, clip_feat=clip, sync_feat=sync)["x"]
+    path = os.path.join(GOLD, "dit_tiny_fp8e4m3_fp32.pt")
+    torch.save({"out": out.float().clone(), "config": "tiny", "shape": dict(B=2, L=50, Lv=8, S=16)}, path)
+    print("wrote", path, len(wrapped), "of", len(linear_like), "modules wrapped", float(out.norm()))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -183,6 +204,7 @@ def main():
         "denoise_midpoint": lambda: gold_denoise(ns, "tiny_midpoint2", 1.0, 6, 1.0, 1, True, "midpoint-2"),
         "denoise_kutta": lambda: gold_denoise(ns, "tiny_kutta4", 1.0, 8, 4.5, 1, True, "kutta-4"),
         "dac_full": lambda: gold_dac_full(ns),
+        "fp8_wrap": lambda: gold_fp8_wrap(ns),
     }
     for k, fn in jobs.items():
         if a.only and a.only != k:
