@@ -52,6 +52,14 @@ extern "C" foley_status foley_debug_flags(uint32_t* out4) {
     return FOLEY_OK;
 }
 
+// In-kernel timeline of the last GEMM launched with dbg_stop == 8 (tools/gemm_micro.py --dbg 8): clock64 stamps.
+extern "C" foley_status foley_debug_times(uint64_t* out16) {
+    unsigned long long h[16];
+    FOLEY_CUDA_OK(cudaMemcpyFromSymbol(h, g_foley_times, sizeof h));
+    for (int i = 0; i < 16; ++i) out16[i] = h[i];
+    return FOLEY_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ engine
 struct foley_engine {
     Engine impl;
@@ -195,6 +203,9 @@ extern "C" foley_status foley_engine_set_option(foley_engine* e, const char* key
         if (value < 1 || value > 8) return fail(FOLEY_ERR_INVALID, "max_splits must be in [1,8]");
         if (e->impl.plan.valid && value > e->impl.max_splits) return fail(FOLEY_ERR_STATE, "raise max_splits before set_conditions");
         e->impl.max_splits_used = static_cast<int>(value);
+        e->impl.graph_valid = false;
+    } else if (k == "debug_skip") {
+        e->impl.debug_skip = static_cast<int>(value);
         e->impl.graph_valid = false;
     } else if (k == "fp8_weight_storage") {
         if (value < 0 || value > 2) return fail(FOLEY_ERR_INVALID, "fp8_weight_storage must be 0 (none), 1 (e4m3fn) or 2 (e5m2)");

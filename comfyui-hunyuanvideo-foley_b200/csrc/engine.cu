@@ -441,6 +441,8 @@ int Engine::pick_splits(int rows, int batch, int n, int kblocks, int bn) const {
 
 foley_status Engine::gemm(cudaStream_t st, const bf16* A, int rows, int batch, long long lda, long long a_bs,
                           const LinearW& W, int n_off, int n_cnt, GemmEpi epi, int splits, int bn) {
+    if (skip_gemm_once) { skip_gemm_once = false; return FOLEY_OK; }          // tools/ablate_step.py only
+    if (debug_skip & (1 << 4)) { if (st == side_stream) return FOLEY_OK; }     // visual-branch GEMMs
     GemmLaunch Lc;
     Lc.a.ptr = A; Lc.a.dtype = DT_BF16; Lc.a.k = W.k; Lc.a.rows = rows; Lc.a.batch = batch; Lc.a.ld = lda;
     Lc.a.batch_stride = a_bs;
@@ -478,6 +480,7 @@ foley_status Engine::proj_combine(cudaStream_t st, const bf16* A, int rows, int 
     ca.split_stride = e.split_stride;
     ca.C = W.n;
     ca.rows_total = rows * batch;
+    if (debug_skip & (1 << 2)) return FOLEY_OK;
     FOLEY_CUDA_OK(launch_k(combine_ln_mod_kernel, dim3(ca.rows_total), dim3(ca.C / 4), 0, st, ca));
     ++launches;
     return FOLEY_OK;
@@ -669,6 +672,7 @@ foley_status Engine::step(cudaStream_t st) {
     };
     auto attn = [&](const bf16* q, const bf16* k, const bf16* v, int Sq, int Sk, long long kv_bs, long long kv_hs,
                     bool cross) -> foley_status {
+        if (debug_skip & 1) return FOLEY_OK;
         AttnArgs a;
         a.q = q; a.k = k; a.v = v; a.o = attn_out; a.H = H; a.Sq = Sq; a.Sk = Sk;
         a.q_batch_stride = static_cast<long long>(Sq) * C; a.q_head_stride = static_cast<long long>(Sq) * 128;
@@ -702,6 +706,7 @@ foley_status Engine::step(cudaStream_t st) {
         FOLEY_CUDA_OK(launch_k(vectok_silu_kernel, dim3(blocks_for(n4, 256)), dim3(256), 0, sm_, a_sync, vec_all, cond_of_grp,
                                trow_of_grp, G, L, C, vectok_act));
         ++launches;
+        skip_gemm_once = (debug_skip >> 3) & 1;
         ST_OK(gemm(sm_, vectok_act, G * L, 1, C, 0, mod_single_all, 0, NS * 6 * C,
                    bf(mod_single, ms_tok, mod_single_all.b, 0), 1, 256));
         if (mod_branch) FOLEY_CUDA_OK(cudaEventRecord(ev_mod, sm_));
@@ -720,11 +725,13 @@ foley_status Engine::step(cudaStream_t st) {
         return FOLEY_OK;
     };
     auto combine_on = [&](cudaStream_t s_, const CombineArgs& ca) -> foley_status {
+        if (debug_skip & (1 << 2)) return FOLEY_OK;
         FOLEY_CUDA_OK(launch_k(combine_ln_mod_kernel, dim3(ca.rows_total), dim3(ca.C / 4), 0, s_, ca));
         ++launches;
         return FOLEY_OK;
     };
     auto qknorm_on = [&](cudaStream_t s_, const QkvArgs& q) -> foley_status {
+        if (debug_skip & (1 << 1)) return FOLEY_OK;
         FOLEY_CUDA_OK(launch_k(qk_norm_rope_kernel, dim3(blocks_for(static_cast<long long>(q.rows_total) * q.n_parts * H, 4)),
                                dim3(128), 0, s_, q));
         ++launches;
@@ -744,7 +751,7 @@ foley_status Engine::step(cudaStream_t st) {
         ST_OK(combine_on(sv, cv));
     }
     const long long jb = static_cast<long long>(Sj) * C, jh = static_cast<long long>(Sj) * 128;
-    for (int i = 0; i < NT; ++i) {
+    for (int i = 0; i < ((debug_skip >> 9) & 1 ? 0 : NT); ++i) {
         const TripleW& w = triple[i];
         // -- joint self attention
         ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.qkv[0], 0, 3 * C, bf(qkv_a, C3, w.qkv[0].b, 0), 1, pick_bn(L, B2, 3 * C, C / 64)));
@@ -822,8 +829,9 @@ foley_status Engine::step(cudaStream_t st) {
     ST_OK(join());   // the side branch must be complete before the step (graph) ends
     // ---- single-stream blocks (hifi_foley.py:364-390)
     const long long sb = static_cast<long long>(L) * C, sh = static_cast<long long>(L) * 128;
-    for (int j = 0; j < NS; ++j) {
+    for (int j = 0; j < ((debug_skip >> 10) & 1 ? 0 : NS); ++j) {
         const SingleW& w = single[j];
+        skip_gemm_once = (debug_skip >> 5) & 1;
         ST_OK(gemm(st, h_a, L, B2, C, sb, w.qkv, 0, 3 * C, bf(qkv_a, C3, w.qkv.b, 0), 1, pick_bn(L, B2, 3 * C, C / 64)));
         {
             QkvArgs q;
@@ -835,16 +843,17 @@ foley_status Engine::step(cudaStream_t st) {
                 q.part[pz].dst = dsts[pz]; q.part[pz].dst_batch_stride = sb; q.part[pz].dst_head_stride = sh;
                 q.part[pz].seq_offset = 0; q.part[pz].norm_w = norms[pz]; q.part[pz].src_col = pz * C;
             }
-            FOLEY_CUDA_OK(launch_k(qk_norm_rope_kernel, dim3(blocks_for(static_cast<long long>(q.rows_total) * 3 * H, 4)), dim3(128), 0, st, q));
-            ++launches;
+            ST_OK(qknorm_on(st, q));
         }
         ST_OK(attn(Qj, Kj, Vj, L, L, sb, sh, false));
         {
             CombineArgs ca;
             ca.bias = w.linear1.b; ca.gate = smod(j); ca.gate_chunk = 2; ca.x = audio; ca.h = h_a; ca.eps = 1e-5f;
             ca.mod = smod(j); ca.shift_chunk = 3; ca.scale_chunk = 4; ca.rm = rm_a;
+            skip_gemm_once = (debug_skip >> 8) & 1;
             ST_OK(proj_combine(st, attn_out, L, B2, C, sb, w.linear1, part_a, ca));
         }
+        skip_gemm_once = (debug_skip >> 6) & 1;
         ST_OK(gemm(st, h_a, L, B2, C, sb, w.w13, 0, 2 * Hs, bf(mlp_a, Hs, nullptr, 0, EPI_SWIGLU), 1, pick_bn(L, B2, 2 * Hs, 3 * C / 64)));
         {
             const bool last = j == NS - 1;
@@ -852,6 +861,7 @@ foley_status Engine::step(cudaStream_t st) {
             ca.gate = smod(j); ca.gate_chunk = 5; ca.x = audio; ca.h = h_a; ca.rm = rm_a;
             if (!last) { ca.eps = 1e-5f; ca.mod = smod(j + 1); ca.shift_chunk = 0; ca.scale_chunk = 1; }
             else { ca.eps = 1e-6f; ca.mod = ModRef(); }   // final LayerNorm, adaLN is a no-op (mlp_layers.py:97-101)
+            skip_gemm_once = (debug_skip >> 7) & 1;
             ST_OK(proj_combine(st, mlp_a, L, B2, Hs, static_cast<long long>(L) * Hs, w.w2, part_a, ca));
         }
     }

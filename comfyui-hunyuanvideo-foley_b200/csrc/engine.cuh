@@ -57,6 +57,8 @@ class Engine {
     int C = 0, H = 0, NT = 0, NS = 0, F = 0, Hs = 0, Hy = 0, LAT = 0;
     int64_t launches = 0;
     bool finalized = false;
+    int debug_skip = 0;           // option "debug_skip": ablation bitmask for tools/ablate_step.py (results are garbage)
+    bool skip_gemm_once = false;
     int fp8_storage = 0;          // option "fp8_weight_storage": the reference's quantization != none for tensors loaded next
     std::unordered_map<std::string, RawTensor> raw;
 

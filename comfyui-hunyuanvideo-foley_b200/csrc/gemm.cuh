@@ -6,8 +6,10 @@
 // [0, rows) read as zero through TMA out-of-bounds fill, which is what gives every sample of a
 // batch its own zero halo for the k=3 / k=7 convolutions and the transposed-conv polyphase form.
 // W is a K-major weight matrix [N, taps*K].  One CTA computes one 128 x BN output tile (optionally one
-// K-split of it): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma
-// issuer, warps 2..9 = epilogue (tcgen05.ld -> registers -> fused epilogue -> global).
+// K-split of it): warp 0 = TMA producer of the weight tiles, warp 10 = TMA producer of the activation tiles (two
+// single-thread producers: one thread issuing both loads of a k-block was the slowest agent of the ring), warp 1 =
+// TMEM allocator + single-thread tcgen05.mma issuer, warps 2..9 = epilogue (tcgen05.ld -> registers -> fused
+// epilogue -> global).
 //
 // Replaces, on the reference path: F.linear / Conv1d(k=1,3) in hifi_foley.py:216-331,364-390,
 // mlp_layers.py:104-149, and the DAC decoder convs in dac.py:28-44,98-149.
@@ -70,7 +72,7 @@ struct GemmCfg {
     static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 3 * 256 * 4 /*epilogue params*/;
-    static constexpr int THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
+    static constexpr int THREADS = 352;   // weight-TMA warp, MMA warp, 8 epilogue warps, activation-TMA warp
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -83,9 +85,9 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 }
 
 template <int BN, bool kTF32, bool kPair = false>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(352, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    const GemmArgs g) {
+                    const __grid_constant__ CUtensorMap tm_c, const GemmArgs g) {
     using Cfg = GemmCfg<BN, kTF32, kPair>;
     extern __shared__ uint8_t smem_raw[];
     // swizzle-128B tiles need 1024-byte alignment
@@ -102,6 +104,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const bool tprobe = g.dbg_stop == 8 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    if (tprobe && threadIdx.x == 0) { g_foley_times[0] = clock64(); g_foley_times[15] = globaltimer_ns(); }
     const int n0 = blockIdx.y * BN;
     const int m_tiles = (g.rows + Cfg::BM - 1) / Cfg::BM;
     const int batch = blockIdx.x / m_tiles;          // x carries (batch, m-tile): it may exceed 65535 (DAC)
@@ -117,12 +121,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const uint32_t pair_rank = kPair ? cluster_ctarank() : 0;
     const bool leader = pair_rank == 0;
 
-    // Each CTA's loads complete on its OWN full barrier; in pair mode the peer forwards "stage landed" to the leader
-    // with one remote arrive per stage (remote complete_tx from TMA, the cta_group::2 TMA form, measured slower here).
-    auto load_b = [&](int i) {
-        const int s = i % Cfg::STAGES;
-        const int kb = kb_begin + i;
-        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+    // Each CTA's loads complete on its OWN full barrier (two arrivals per phase: the weight producer's and the
+    // activation producer's expect_tx); in pair mode the peer forwards "stage landed" to the leader with one remote
+    // arrive per stage (remote complete_tx from TMA, the cta_group::2 TMA form, measured slower here).
+    auto load_b = [&](int s, int kb) {
+        mbar_expect_tx(&full_bar[s], Cfg::B_BYTES);
         tma_load_3d(smem_b + s * Cfg::B_BYTES, &tm_b, &full_bar[s], kb * Cfg::BK,
                     n0 + static_cast<int>(pair_rank) * Cfg::B_ROWS, 0);   // rank-3 map; pair: this CTA's half
     };
@@ -131,8 +134,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
         tma_prefetch_desc(&tm_b);
+        tma_prefetch_desc(&tm_c);
         for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], 2);
             mbar_init(&empty_bar[s], 1);
             mbar_init(&peer_ready[s], 1);
         }
@@ -141,7 +145,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // Weights do not depend on the previous kernel (programmatic dependent launch) nor on the TMEM allocation
         // going on in warp 1: fill the ring with B tiles right away so the weight stream's latency hides under the
         // rest of the prologue and under the predecessor kernel's tail.
-        for (int i = 0; i < pre; ++i) load_b(i);
+        for (int i = 0; i < pre; ++i) load_b(i, kb_begin + i);
     } else if (warp == 1) {
         if constexpr (kPair) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr_smem);
         else tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
@@ -151,50 +155,62 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     if constexpr (kPair) cluster_sync_all();   // the peer's barriers must exist before anything is signalled to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (tprobe && threadIdx.x == 0) g_foley_times[1] = clock64();
 
     if (g.dbg_stop == 1) {
         // setup / teardown only
     } else if (warp == 0) {
-        // ------------------------------------------------------------- TMA producer
+        // ------------------------------------------------------------- TMA producer: weight tiles past the first ring pass
         if (lane == 0) {
-            auto load_a = [&](int i) {
-                const int s = i % Cfg::STAGES;
-                const int kb = kb_begin + i;
-                const int tap = kb / g.kb_per_tap;
-                const int kcol = (kb - tap * g.kb_per_tap) * Cfg::BK;
-                const int arow = m0 + g.tap_off0 + tap * g.tap_stride;
-                tma_load_3d(smem_a + s * Cfg::A_BYTES, &tm_a, &full_bar[s], kcol, arow, batch);
-            };
+            int s = 0;
+            uint32_t ph = 1;   // round r >= 1 waits for the consumer's release of round r-1: parity (r & 1) ^ 1
+            for (int i = pre; i < num_kb; ++i) {
+                if (!mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + i)) break;
+                load_b(s, kb_begin + i);
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 10) {
+        // ------------------------------------------------------------- TMA producer: activation tiles
+        if (lane == 0) {
+            int tap = kb_begin / g.kb_per_tap;
+            int kk = kb_begin - tap * g.kb_per_tap;
+            int arow = m0 + g.tap_off0 + tap * g.tap_stride;
+            int s = 0;
+            uint32_t ph = 0;
             pdl_wait();   // activations (A) are the predecessor's output
+            if (tprobe) g_foley_times[2] = clock64();
             for (int i = 0; i < num_kb; ++i) {
-                if (i >= pre) {
-                    const int s = i % Cfg::STAGES;
-                    const uint32_t ph = (i / Cfg::STAGES) & 1;
-                    if (!mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + i)) break;
-                    load_b(i);
-                }
-                load_a(i);
+                if (i >= Cfg::STAGES) { if (!mbar_wait(&empty_bar[s], ph ^ 1, 0x180 + i)) break; }
+                mbar_expect_tx(&full_bar[s], Cfg::A_BYTES);
+                tma_load_3d(smem_a + s * Cfg::A_BYTES, &tm_a, &full_bar[s], kk * Cfg::BK, arow, batch);
+                if (++kk == g.kb_per_tap) { kk = 0; arow += g.tap_stride; }
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------- MMA issuer (one thread; pair: leader CTA only)
         if (lane == 0 && !leader) {
             // peer CTA of a pair: forward each landed stage to the leader
+            int s = 0;
+            uint32_t ph = 0;
             for (int i = 0; i < num_kb; ++i) {
-                const int s = i % Cfg::STAGES;
-                const uint32_t ph = (i / Cfg::STAGES) & 1;
                 if (!mbar_wait(&full_bar[s], ph, 0x400 + i)) break;
                 mbar_arrive_cluster(mapa_u32(smem_u32(&peer_ready[s]), 0));
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
             }
         }
         if (lane == 0 && leader) {
             constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, kPair ? 2 * Cfg::BM : Cfg::BM, BN);
+            int s = -1;
+            uint32_t ph = 1;
             for (int i = 0; i < num_kb; ++i) {
-                const int s = i % Cfg::STAGES;
-                const uint32_t ph = (i / Cfg::STAGES) & 1;
+                if (++s == Cfg::STAGES) s = 0;
+                if (s == 0) ph ^= 1;
                 if (!mbar_wait(&full_bar[s], ph, 0x200 + i)) break;
                 if constexpr (kPair) { if (!mbar_wait(&peer_ready[s], ph, 0x500 + i)) break; }
                 tc_fence_after();
+                if (tprobe && i == 0) g_foley_times[3] = clock64();
                 if (g.dbg_stop == 2) {
                     if constexpr (kPair) { mbar_arrive(&empty_bar[s]); mbar_arrive_cluster(mapa_u32(smem_u32(&empty_bar[s]), 1)); }
                     else mbar_arrive(&empty_bar[s]);
@@ -225,6 +241,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 if constexpr (kPair) umma_commit_pair(tmem_full_bar);   // accumulators complete in both CTAs
                 else umma_commit(tmem_full_bar);
             }
+            if (tprobe) g_foley_times[4] = clock64();
         }
     } else {
         // ------------------------------------------------------------- epilogue warps (2..9)
@@ -253,14 +270,102 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         pdl_wait();                          // outputs may alias buffers the predecessor still reads
+        // (Parking these warps in a hardware barrier until warp 1 has seen the accumulator barrier, instead of letting
+        // all of them poll it through the mainloop, measured no difference: try_wait suspends in hardware.)
         const bool acc_ok = mbar_wait(tmem_full_bar, 0, 0x300);
         pdl_trigger();                       // mainloop done: the next kernel may start its prologue
         tc_fence_after();
+        if (tprobe && threadIdx.x == 64) g_foley_times[5] = clock64();
         const bool row_ok = r < g.rows;
         const long long row_off = static_cast<long long>(batch) * e.out_batch_stride +
                                   static_cast<long long>(r) * e.ldo;
+        if (e.mode != EPI_DAC && !(BN == 64 && e.mode == EPI_SWIGLU)) {   // (a 64-wide SwiGLU tile is half a store box)
+            // ---- DiT epilogues: the tile goes through shared memory (the idle operand ring) and leaves as TMA stores.
+            // A thread owns one accumulator ROW, so direct stores made every warp instruction touch 32 different
+            // lines (measured 2.5-6.5 us per tile, LSU-transaction bound); staged, the tile is written to global as
+            // whole 128-byte lines by the copy engine while the warps move on.  Staging layout = TMA boxes of
+            // 128 rows x 128 B with the 128-byte swizzle (16-byte piece index ^ (row & 7)): conflict-free for one
+            // row per thread.  bpc = output bytes per accumulator column: 4 (fp32 partials), 2 (bf16), 1 (SwiGLU pairs).
+            const int bpc = e.mode == EPI_F32 ? 4 : (e.mode == EPI_BF16 ? 2 : 1);
+            const int esz = e.mode == EPI_F32 ? 4 : 2;
+            const int n_out = e.mode == EPI_SWIGLU ? g.n >> 1 : g.n;
+            const uint32_t r_local = static_cast<uint32_t>(q * 32 + lane);
+            const uint32_t stage_base = smem_u32(smem);
+            const bool live = acc_ok && (g.dbg_stop & 7) == 0 && num_kb > 0;
+            int boxes_issued = 0;
+            constexpr int NIT = BN / 64;
+            // One accumulator chunk (32 columns of this thread's row) -> fused math -> swizzled staging row.
+            auto emit = [&](const uint32_t (&v)[32], int c0) {
+                const float* pb = epi_f + c0;
+                const uint32_t byte_off = static_cast<uint32_t>(c0 * bpc);
+                const uint32_t row_addr = stage_base + (byte_off >> 7) * 16384u + r_local * 128u;
+                const uint32_t piece0 = (byte_off & 127u) >> 4;
+                const uint32_t sw = r_local & 7u;
+                if (e.mode == EPI_F32) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_v4(row_addr + (((piece0 + j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else if (e.mode == EPI_BF16) {
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float a0 = __uint_as_float(v[j]) + pb[j], a1 = __uint_as_float(v[j + 1]) + pb[j + 1];
+                        if (e.act == ACT_SILU) {
+                            a0 = bf16_round(a0); a1 = bf16_round(a1);
+                            a0 = __fdividef(a0, 1.0f + __expf(-a0));
+                            a1 = __fdividef(a1, 1.0f + __expf(-a1));
+                        } else if (e.act != ACT_NONE) {
+                            a0 = apply_act(bf16_round(a0), e.act);
+                            a1 = apply_act(bf16_round(a1), e.act);
+                        }
+                        packed[j >> 1] = pack_bf16x2(a0, a1);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        st_shared_v4(row_addr + (((piece0 + j) ^ sw) << 4), packed[4 * j], packed[4 * j + 1],
+                                     packed[4 * j + 2], packed[4 * j + 3]);
+                } else {   // EPI_SWIGLU
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float g0 = bf16_round(__uint_as_float(v[j])), u0 = bf16_round(__uint_as_float(v[j + 1]));
+                        const float g1 = bf16_round(__uint_as_float(v[j + 2])), u1 = bf16_round(__uint_as_float(v[j + 3]));
+                        const float s0 = bf16_round(__fdividef(g0, 1.0f + __expf(-g0))) * u0;
+                        const float s1 = bf16_round(__fdividef(g1, 1.0f + __expf(-g1))) * u1;
+                        packed[j >> 2] = pack_bf16x2(s0, s1);
+                    }
+                    st_shared_v4(row_addr + (((piece0 + 0) ^ sw) << 4), packed[0], packed[1], packed[2], packed[3]);
+                    st_shared_v4(row_addr + (((piece0 + 1) ^ sw) << 4), packed[4], packed[5], packed[6], packed[7]);
+                }
+            };
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32;
+#pragma unroll 1   // (fully unrolled, the three fused epilogues x four chunks ran 40 % slower: measured)
+            for (int it = 0; it < NIT; ++it) {
+                const int c0 = half * 32 + it * 64;
+                if (live && n0 + c0 < g.n) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + it * 64, v);
+                    tmem_ld_wait();
+                    emit(v, c0);
+                }
+                {   // every 64-column group leaves as soon as all eight warps have written it
+                    fence_proxy_async();                          // generic-proxy smem writes -> visible to the TMA store
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (threadIdx.x == 64 && live) {
+                        const int boxes_done = ((it + 1) * 64 * bpc) >> 7;
+                        for (; boxes_issued < boxes_done; ++boxes_issued) {
+                            const int col_elem = (n0 * bpc + boxes_issued * 128) / esz;
+                            if (col_elem < n_out)
+                                tma_store_4d(&tm_c, smem + boxes_issued * 16384, col_elem, m0, batch, split);
+                        }
+                        tma_store_commit();
+                    }
+                }
+            }
+            if (threadIdx.x == 64) tma_store_wait_read();         // the staging memory must outlive the reads
+        } else
 #pragma unroll 1
-        for (int c0 = half * 32; c0 < BN && acc_ok && g.dbg_stop == 0; c0 += 64) {
+        for (int c0 = half * 32; c0 < BN && acc_ok && (g.dbg_stop & 7) == 0; c0 += 64) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
             tmem_ld_wait();
@@ -367,13 +472,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         }
     }
 
+    if (tprobe && threadIdx.x == 64) g_foley_times[6] = clock64();
     tc_fence_before();
     __syncthreads();
+    if (tprobe && threadIdx.x == 0) g_foley_times[7] = clock64();
     if constexpr (kPair) cluster_sync_all();   // the peer may still read this CTA's B half / signal its barriers
     if (warp == 1) {
         tc_fence_after();
         if constexpr (kPair) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
         else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        if (tprobe && lane == 0) { g_foley_times[8] = clock64(); g_foley_times[14] = globaltimer_ns(); }
     }
 }
 

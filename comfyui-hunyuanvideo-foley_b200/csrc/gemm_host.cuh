@@ -88,6 +88,43 @@ inline bool encode_operand_map(CUtensorMap* out, const Operand& t, int box_rows,
     return true;
 }
 
+// Output view of the DiT epilogues for the TMA-store path: element (split, b, r, c) at out + split*split_stride +
+// b*batch_stride + r*ld + c.  Box = 128 rows x 128 bytes, 128-byte swizzle (the staging layout of the epilogue).
+inline bool encode_out_map(CUtensorMap* out, void* ptr, bool f32, long long n_out, long long rows, long long batch,
+                           long long splits, long long ld, long long batch_stride, long long split_stride,
+                           std::string* err) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) { if (err) *err = "cuTensorMapEncodeTiled entry point unavailable"; return false; }
+    const int esz = f32 ? 4 : 2;
+    if (batch < 1) batch = 1;
+    if (splits < 1) splits = 1;
+    if (batch_stride <= 0) batch_stride = rows * ld;
+    if (split_stride <= 0) split_stride = batch * batch_stride;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(n_out), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch),
+                          static_cast<cuuint64_t>(splits)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * esz, static_cast<cuuint64_t>(batch_stride) * esz,
+                             static_cast<cuuint64_t>(split_stride) * esz};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(128 / esz), 128, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15)) {
+        if (err) *err = "GEMM output must be 16-byte aligned (pointer and strides)";
+        return false;
+    }
+    CUresult r = enc(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(out) failed (%d): n=%lld rows=%lld batch=%lld splits=%lld ld=%lld",
+                     static_cast<int>(r), n_out, rows, batch, splits, ld);
+            *err = buf;
+        }
+        return false;
+    }
+    return true;
+}
+
 // Programmatic dependent launch for every engine kernel (FOLEY_PDL=0 disables).
 inline bool pdl_enabled() {
     static int v = -1;
@@ -149,8 +186,8 @@ struct GemmLaunch {
 };
 
 template <int BN, bool kTF32, bool kPair = false>
-inline cudaError_t launch_gemm_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& args,
-                                    dim3 grid, cudaStream_t stream) {
+inline cudaError_t launch_gemm_inst(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
+                                    const GemmArgs& args, dim3 grid, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, kTF32, kPair>;
     auto kern = gemm_tcgen05_kernel<BN, kTF32, kPair>;
     const int cx = kPair ? 2 : 1, cy = 1;
@@ -185,7 +222,7 @@ inline cudaError_t launch_gemm_inst(const CUtensorMap& ma, const CUtensorMap& mb
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, kern, ma, mb, args);
+    return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, args);
 }
 
 // Opts every instantiation into its dynamic shared-memory size up front (must not happen lazily inside a
@@ -230,8 +267,16 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
     wb.ld = wb.k; wb.batch_stride = wb.k * wb.rows;
     if (!encode_operand_map(&mb, wb, pair ? L.bn / 2 : L.bn, err)) return false;
 
-    GemmArgs args;
     const long long out_rows = L.out_rows > 0 ? L.out_rows : L.a.rows;
+    CUtensorMap mc = ma;   // EPI_DAC stores directly; the DiT epilogues leave through TMA stores
+    if (L.epi.mode != EPI_DAC) {
+        const bool f32 = L.epi.mode == EPI_F32;
+        if (!encode_out_map(&mc, L.epi.out, f32, L.epi.mode == EPI_SWIGLU ? L.n / 2 : L.n, out_rows,
+                            L.a.batch > 0 ? L.a.batch : 1, L.splits < 1 ? 1 : L.splits, L.epi.ldo, L.epi.out_batch_stride,
+                            L.epi.split_stride, err))
+            return false;
+    }
+    GemmArgs args;
     args.rows = static_cast<int>(out_rows);
     args.n = static_cast<int>(L.n);
     args.kb_per_tap = static_cast<int>(L.a.k / bk);
@@ -248,17 +293,17 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
               static_cast<unsigned>(((nt + cy - 1) / cy) * cy), static_cast<unsigned>(args.splits));
     cudaError_t e = cudaSuccess;
     if (!tf32) {
-        if (L.bn == 64) e = launch_gemm_inst<64, false>(ma, mb, args, grid, stream);
-        else if (L.bn == 128) e = pair ? launch_gemm_inst<128, false, true>(ma, mb, args, grid, stream)
-                                       : launch_gemm_inst<128, false>(ma, mb, args, grid, stream);
-        else if (L.bn == 256) e = pair ? launch_gemm_inst<256, false, true>(ma, mb, args, grid, stream)
-                                       : launch_gemm_inst<256, false>(ma, mb, args, grid, stream);
+        if (L.bn == 64) e = launch_gemm_inst<64, false>(ma, mb, mc, args, grid, stream);
+        else if (L.bn == 128) e = pair ? launch_gemm_inst<128, false, true>(ma, mb, mc, args, grid, stream)
+                                       : launch_gemm_inst<128, false>(ma, mb, mc, args, grid, stream);
+        else if (L.bn == 256) e = pair ? launch_gemm_inst<256, false, true>(ma, mb, mc, args, grid, stream)
+                                       : launch_gemm_inst<256, false>(ma, mb, mc, args, grid, stream);
         else { if (err) *err = "unsupported BN"; return false; }
     } else {
-        if (L.bn == 64) e = launch_gemm_inst<64, true>(ma, mb, args, grid, stream);
-        else if (L.bn == 128) e = launch_gemm_inst<128, true>(ma, mb, args, grid, stream);
-        else if (L.bn == 256) e = pair ? launch_gemm_inst<256, true, true>(ma, mb, args, grid, stream)
-                                       : launch_gemm_inst<256, true>(ma, mb, args, grid, stream);
+        if (L.bn == 64) e = launch_gemm_inst<64, true>(ma, mb, mc, args, grid, stream);
+        else if (L.bn == 128) e = launch_gemm_inst<128, true>(ma, mb, mc, args, grid, stream);
+        else if (L.bn == 256) e = pair ? launch_gemm_inst<256, true, true>(ma, mb, mc, args, grid, stream)
+                                       : launch_gemm_inst<256, true>(ma, mb, mc, args, grid, stream);
         else { if (err) *err = "unsupported BN"; return false; }
     }
     if (e != cudaSuccess) {

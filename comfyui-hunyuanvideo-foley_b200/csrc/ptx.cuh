@@ -56,6 +56,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Debug words: [0] = code of the first mbarrier wait that timed out (0 = none).
 __device__ unsigned int g_foley_dbg[4];
+// In-kernel timeline probe (GEMM dbg_stop == 8, CTA 0 only): clock64 stamps, [15] = %globaltimer at entry, [14] at exit.
+__device__ unsigned long long g_foley_times[16];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // Bounded spin: a mis-programmed pipeline records a code and bails out instead of hanging the box.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsigned int code = 1) {
     uint32_t spins = 0;
@@ -90,6 +97,20 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)),
           "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+
+// TMA store of one box from shared memory (bulk async group); out-of-bounds parts of the box are not written.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Source (shared memory) reads of all committed bulk stores are done; the global writes complete with the grid.
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // ----------------------------------------------------------------------------- programmatic dependent launch
@@ -268,9 +289,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_tanh_f(float x) {
+    // tanh(u) = 1 - 2 / (1 + e^{2u}) on the fast exp / divide units (abs error ~1e-6, far below the bf16 rounding
+    // that follows); saturates correctly: e^{2u} -> inf gives 1, -> 0 gives -1.
     const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-    float inner = k0 * (x + k1 * x * x * x);
-    return 0.5f * x * (1.0f + tanhf(inner));
+    const float inner = k0 * (x + k1 * x * x * x);
+    const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * inner));
+    return 0.5f * x * (1.0f + t);
 }
 
 }  // namespace foley

@@ -9,7 +9,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfoley_b200.so")
+LIB_PATH = os.environ.get("FOLEY_B200_LIB", os.path.join(_HERE, "libfoley_b200.so"))   # override: A/B builds only
 
 FOLEY_DT = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2, torch.float8_e4m3fn: 3, torch.float8_e5m2: 4}
 FP8_STORAGE = {"none": 0, None: 0, "fp8_e4m3fn": 1, "fp8_e5m2": 2}   # option "fp8_weight_storage"

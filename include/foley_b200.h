@@ -146,6 +146,11 @@ foley_status foley_debug_read(foley_engine* e, const char* what, float* dst, int
 
 /* Reads and clears device debug words: out4[0] = code of the first pipeline wait that timed out (0 = none). */
 foley_status foley_debug_flags(uint32_t* out4);
+/* Timeline stamps (SM clock cycles; [15]/[14] = %globaltimer ns at entry/exit) of CTA 0 of the last foley_gemm launched
+ * with the bring-up selector 8 in the upper bits of `bn`: [0] entry, [1] prologue done, [2] activations released by
+ * the predecessor, [3] first stage landed, [4] last MMA issued, [5] accumulator complete, [6] epilogue stores issued,
+ * [7] CTA joined, [8] TMEM released. */
+foley_status foley_debug_times(uint64_t* out16);
 /* Runtime switches: "cuda_graph" (0/1, default 1), "max_splits" (1..8, default 8), "fp8_weight_storage" (0 none /
  * 1 e4m3fn / 2 e5m2; applies to tensors loaded AFTER the call: the Linear / Conv weights the reference would keep in
  * FP8 are rounded through that format, so results match the reference's quantization setting; compute stays bf16). */

@@ -22,9 +22,10 @@ ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--all", action="store_true")
 ap.add_argument("--dbg", type=int, default=0, help="partial pipeline: 2 = TMA only, 3 = TMA+MMA (no epilogue)")
 a = ap.parse_args()
-lib = ctypes.CDLL(os.path.join(ROOT, "comfyui-hunyuanvideo-foley_b200", "libfoley_b200.so"))
+lib = ctypes.CDLL(os.environ.get("FOLEY_B200_LIB", os.path.join(ROOT, "comfyui-hunyuanvideo-foley_b200", "libfoley_b200.so")))
 lib.foley_last_error.restype = ctypes.c_char_p
 i64, i32, vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p
+lib.foley_debug_times.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
 lib.foley_gemm.argtypes = [vp, i32, i64, i64, i64, i64, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, i64, i64,
                            i64, vp]
 c = SY.model_config(a.model)
@@ -65,6 +66,19 @@ def run(name, bn):
     us = e0.elapsed_time(e1) * 1e3 / a.iters
     fl = 2.0 * B2 * L * K * taps * N
     print(f"{name:5s} K={K}x{taps} N={N} bn={bn} splits={sp}: {us:7.1f} us  {fl / us / 1e6:7.1f} TFLOP/s", flush=True)
+    if a.dbg == 8:
+        t = (ctypes.c_uint64 * 16)()
+        lib.foley_debug_times(t)
+        t = list(t)
+        wall_ns = t[14] - t[15]
+        cyc = t[8] - t[0]
+        ghz = cyc / max(wall_ns, 1)
+        names = ["prologue", "A released (PDL wait)", "first stage landed", "last MMA issued", "accumulator complete",
+                 "epilogue done", "CTA joined", "TMEM released"]
+        marks = [t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]]
+        print(f"      CTA0 timeline: {wall_ns} ns wall, {cyc} cycles ({ghz:.2f} GHz); cumulative ns:")
+        for nm, m in zip(names, marks):
+            print(f"        {nm:28s} {(m - t[0]) / ghz:8.0f}")
 
 
 if a.all:
