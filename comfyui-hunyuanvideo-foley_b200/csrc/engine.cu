@@ -615,8 +615,8 @@ foley_status Engine::prepare_timesteps(const float* t_host, int n_t, bool per_sa
         ST_OK(palloc(&mod_triple, static_cast<size_t>(p.n_t) * NT * 18 * C));
         ST_OK(palloc(&t_dev, p.n_t));
         ST_OK(palloc(&sigmas_dev, p.n_t + 1));
-        ST_OK(palloc(&vectok_act, static_cast<size_t>(p.G) * p.L * C));
-        ST_OK(palloc(&mod_single, static_cast<size_t>(p.G) * p.L * NS * 6 * C));
+        ST_OK(palloc(&vectok_act, static_cast<size_t>(p.G) * p.S * C));
+        ST_OK(palloc(&mod_single, static_cast<size_t>(p.G) * p.S * NS * 6 * C));
         ST_OK(palloc(&sc_e, static_cast<size_t>(p.n_t) * cfg.freq_dim));
         ST_OK(palloc(&sc_h1, static_cast<size_t>(p.n_t) * C));
         ST_OK(palloc(&sc_vs, static_cast<size_t>(p.n_t) * C));
@@ -663,9 +663,14 @@ foley_status Engine::step(cudaStream_t st) {
         ModRef m; m.base = mod_triple + (static_cast<long long>(blk) * 2 + stream) * 9 * C; m.sample_stride = mt_stride;
         m.tok_stride = 0; m.by_trow = 1; return m;
     };
+    // Single-block modulation vectors are per token, but the per-token condition is the nearest-exact up-sampling of
+    // the S sync tokens (hifi_foley.py:755-762): audio token l carries a copy of sync token idx[l].  They are computed
+    // once per SYNC token (S ~ L/2 rows) and looked up through the index table — less than half of the reference's
+    // modulation FLOPs (13 % of the step) for bit-identical values.
+    const int S = p.S;
     auto smod = [&](int blk) {
-        ModRef m; m.base = mod_single + static_cast<long long>(blk) * 6 * C; m.sample_stride = ms_tok * L;
-        m.tok_stride = ms_tok; m.by_trow = 0; return m;
+        ModRef m; m.base = mod_single + static_cast<long long>(blk) * 6 * C; m.sample_stride = ms_tok * S;
+        m.tok_stride = ms_tok; m.by_trow = 0; m.tok_map = sc_idx; return m;
     };
     auto bf = [&](bf16* out, long long ldo, const bf16* bias, int act, int mode = EPI_BF16) {
         GemmEpi e; e.mode = mode; e.act = act; e.out = out; e.ldo = ldo; e.bias = bias; return e;
@@ -702,12 +707,12 @@ foley_status Engine::step(cudaStream_t st) {
             FOLEY_CUDA_OK(cudaEventRecord(ev_fork, st));
             FOLEY_CUDA_OK(cudaStreamWaitEvent(sm_, ev_fork, 0));
         }
-        const long long n4 = static_cast<long long>(G) * L * C / 4;
-        FOLEY_CUDA_OK(launch_k(vectok_silu_kernel, dim3(blocks_for(n4, 256)), dim3(256), 0, sm_, a_sync, vec_all, cond_of_grp,
-                               trow_of_grp, G, L, C, vectok_act));
+        const long long n4 = static_cast<long long>(G) * S * C / 4;
+        FOLEY_CUDA_OK(launch_k(vectok_silu_kernel, dim3(blocks_for(n4, 256)), dim3(256), 0, sm_, sc_s3, vec_all, cond_of_grp,
+                               trow_of_grp, G, S, C, vectok_act));
         ++launches;
         skip_gemm_once = (debug_skip >> 3) & 1;
-        ST_OK(gemm(sm_, vectok_act, G * L, 1, C, 0, mod_single_all, 0, NS * 6 * C,
+        ST_OK(gemm(sm_, vectok_act, G * S, 1, C, 0, mod_single_all, 0, NS * 6 * C,
                    bf(mod_single, ms_tok, mod_single_all.b, 0), 1, 256));
         if (mod_branch) FOLEY_CUDA_OK(cudaEventRecord(ev_mod, sm_));
     }

@@ -164,7 +164,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 1;   // round r >= 1 waits for the consumer's release of round r-1: parity (r & 1) ^ 1
-            for (int i = pre; i < num_kb; ++i) {
+            for (int i = pre; i < (g.dbg_stop == 4 ? 0 : num_kb); ++i) {
                 if (!mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + i)) break;
                 load_b(s, kb_begin + i);
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
@@ -180,7 +180,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             uint32_t ph = 0;
             pdl_wait();   // activations (A) are the predecessor's output
             if (tprobe) g_foley_times[2] = clock64();
-            for (int i = 0; i < num_kb; ++i) {
+            for (int i = 0; i < (g.dbg_stop == 4 ? pre : num_kb); ++i) {
                 if (i >= Cfg::STAGES) { if (!mbar_wait(&empty_bar[s], ph ^ 1, 0x180 + i)) break; }
                 mbar_expect_tx(&full_bar[s], Cfg::A_BYTES);
                 tma_load_3d(smem_a + s * Cfg::A_BYTES, &tm_a, &full_bar[s], kk * Cfg::BK, arow, batch);
@@ -207,8 +207,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             for (int i = 0; i < num_kb; ++i) {
                 if (++s == Cfg::STAGES) s = 0;
                 if (s == 0) ph ^= 1;
+                if (g.dbg_stop != 4 || i < pre) {   // dbg 4: MMA-only rate, the first ring pass is re-used without reloading
                 if (!mbar_wait(&full_bar[s], ph, 0x200 + i)) break;
                 if constexpr (kPair) { if (!mbar_wait(&peer_ready[s], ph, 0x500 + i)) break; }
+                }
                 tc_fence_after();
                 if (tprobe && i == 0) g_foley_times[3] = clock64();
                 if (g.dbg_stop == 2) {

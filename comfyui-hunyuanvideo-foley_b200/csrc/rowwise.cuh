@@ -19,6 +19,7 @@ struct ModRef {
     long long sample_stride = 0;
     long long tok_stride = 0;
     int by_trow = 0;
+    const int* tok_map = nullptr;   // per-token vectors stored once per SOURCE token: row of token l is tok_map[l]
 };
 
 struct RowMap {
@@ -31,7 +32,8 @@ struct RowMap {
 __device__ __forceinline__ const __nv_bfloat16* mod_ptr(const ModRef& m, const RowMap& rm, int b, int l, int chunk, int C) {
     const int g = rm.grp_of_sample[b];
     const long long s = m.by_trow ? rm.trow_of_grp[g] : g;
-    return m.base + s * m.sample_stride + static_cast<long long>(l) * m.tok_stride + static_cast<long long>(chunk) * C;
+    const int lt = m.tok_map ? m.tok_map[l] : l;
+    return m.base + s * m.sample_stride + static_cast<long long>(lt) * m.tok_stride + static_cast<long long>(chunk) * C;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
