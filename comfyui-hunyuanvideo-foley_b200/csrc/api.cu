@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "engine.cuh"
 #include "gemm_host.cuh"
+#include "preprocess.cuh"
 #include "safetensors.cuh"
 
 namespace foley {
@@ -72,6 +73,34 @@ struct foley_engine {
     } catch (const std::exception& ex) {                                       \
         return fail(FOLEY_ERR_CUDA, std::string("internal error: ") + ex.what()); \
     }
+
+extern "C" foley_status foley_preprocess_frames(const float* image, int32_t n_frames, int32_t H, int32_t W,
+                                                const int32_t* frame_idx, int32_t T, int32_t resize_h, int32_t resize_w,
+                                                int32_t crop_top, int32_t crop_left, int32_t out_h, int32_t out_w,
+                                                float* out, void* stream) {
+    API_GUARD_BEGIN
+    return preprocess_frames(image, n_frames, H, W, frame_idx, T, resize_h, resize_w, crop_top, crop_left, out_h, out_w, out,
+                             static_cast<cudaStream_t>(stream));
+    API_GUARD_END
+}
+
+// The int16 filter bank of one axis, host only (tests compare it with the oracle's / ATen's).
+extern "C" foley_status foley_resize_weights(int32_t in_size, int32_t out_size, int32_t* xmin, int32_t* xsize, int16_t* w,
+                                             int64_t w_cap, int32_t* max_interp, int32_t* precision) {
+    if (in_size < 1 || out_size < 1) return fail(FOLEY_ERR_INVALID, "foley_resize_weights: empty axis");
+    API_GUARD_BEGIN
+    const ResizeBank b = make_resize_bank(in_size, out_size);
+    if (max_interp) *max_interp = b.max_interp;
+    if (precision) *precision = b.precision;
+    if (w && static_cast<int64_t>(b.w.size()) > w_cap) return fail(FOLEY_ERR_INVALID, "foley_resize_weights: weight buffer too small");
+    for (int i = 0; i < out_size; ++i) {
+        if (xmin) xmin[i] = b.xmin[i];
+        if (xsize) xsize[i] = b.xsize[i];
+    }
+    if (w) std::copy(b.w.begin(), b.w.end(), w);
+    return FOLEY_OK;
+    API_GUARD_END
+}
 
 extern "C" foley_status foley_engine_create(const foley_config* cfg, int device, foley_engine** out) {
     if (!cfg || !out) return fail(FOLEY_ERR_INVALID, "foley_engine_create: null argument");

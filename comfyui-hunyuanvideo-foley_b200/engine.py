@@ -51,6 +51,10 @@ def load_library(path=None):
     lib.foley_safetensors_probe.argtypes = [c_char_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]
     lib.foley_fp8_wraps.argtypes = [c_char_p, c_int32]
     lib.foley_fp8_wraps.restype = c_int32
+    lib.foley_preprocess_frames.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(c_int32), c_int32, c_int32, c_int32,
+                                            c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    lib.foley_resize_weights.argtypes = [c_int32, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(ctypes.c_int16),
+                                         c_int64, POINTER(c_int32), POINTER(c_int32)]
     lib.foley_engine_finalize.argtypes = [c_void_p]
     lib.foley_set_conditions.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_int32, c_void_p]

@@ -11,7 +11,6 @@ import torch
 
 
 def load_reference_extractors(synchformer_path, device):
-    from torchvision.transforms import v2
     from transformers import AutoModel, AutoTokenizer, ClapTextModelWithProjection
     from hunyuanvideo_foley.models.synchformer import Synchformer          # reference package, if installed
     from hunyuanvideo_foley.utils.feature_utils import (encode_text_feat, encode_video_with_siglip2,
@@ -28,23 +27,18 @@ def load_reference_extractors(synchformer_path, device):
         "clap_model": ClapTextModelWithProjection.from_pretrained("laion/larger_clap_general").to(device).eval(),
         "device": device,
     })
-    siglip2_pre = v2.Compose([v2.Resize((512, 512), interpolation=v2.InterpolationMode.BICUBIC, antialias=True),
-                              v2.ToDtype(torch.float32, scale=True), v2.Normalize([0.5] * 3, [0.5] * 3)])
-    sync_pre = v2.Compose([v2.Resize(224, interpolation=v2.InterpolationMode.BICUBIC, antialias=True),
-                           v2.CenterCrop(224), v2.ToDtype(torch.float32, scale=True),
-                           v2.Normalize([0.5] * 3, [0.5] * 3)])
-
-    def extract_features(frames_8fps, frames_25fps, prompt, negative_prompt):
+    def extract_features(pre_8fps, pre_25fps, prompt, negative_prompt):
+        """pre_8fps [T8,3,512,512] / pre_25fps [T25,3,224,224]: encoder inputs already preprocessed on the GPU by
+        preprocess.preprocess_video (the Sampler does that when `preprocessed_inputs` is set), or None for text-to-audio."""
         visual, audio_len = {}, None
-        if frames_8fps is not None:
-            x8 = torch.stack([siglip2_pre(f) for f in frames_8fps]).unsqueeze(0).to(device)
-            x25 = torch.stack([sync_pre(f) for f in frames_25fps]).unsqueeze(0).to(device)
-            visual["siglip2_feat"] = encode_video_with_siglip2(x8, deps)
-            visual["syncformer_feat"] = encode_video_with_sync(x25, deps)
-            audio_len = frames_25fps.shape[0] / 25.0
+        if pre_8fps is not None:
+            visual["siglip2_feat"] = encode_video_with_siglip2(pre_8fps.unsqueeze(0).to(device), deps)
+            visual["syncformer_feat"] = encode_video_with_sync(pre_25fps.unsqueeze(0).to(device), deps)
+            audio_len = pre_25fps.shape[0] / 25.0
         feats, _ = encode_text_feat([negative_prompt, prompt], deps)
         return visual, {"text_feat": feats[1:], "uncond_text_feat": feats[:1]}, audio_len
 
     out = dict(deps)
     out["extract_features"] = extract_features
+    out["preprocessed_inputs"] = True
     return out

@@ -249,7 +249,7 @@ class HunyuanDependenciesLoader:
 # --------------------------------------------------------------------------------------------------------
 def resample_frame_indices(num_frames_to_process, duration, fps):
     """torch.linspace(0, n-1, int(duration*fps)).long() — the reference's frame pick (nodes.py:310,315)."""
-    return torch.linspace(0, num_frames_to_process - 1, int(duration * fps)).long()
+    return torch.linspace(0, num_frames_to_process - 1, int(duration * fps)).long()   # (same rule: preprocess.py)
 
 
 def t2a_feature_lengths(duration):
@@ -309,7 +309,13 @@ class HunyuanFoleySampler:
         extract = hunyuan_deps.get("extract_features") if isinstance(hunyuan_deps, dict) else None
         if extract is None:
             raise FoleyError("hunyuan_deps carries no feature extractors (see HunyuanDependenciesLoader)")
-        if image is not None:
+        if image is not None and hunyuan_deps.get("preprocessed_inputs", False):
+            # frames -> encoder inputs on the GPU (quantise, 8 / 25 fps picks, antialiased bicubic resize, crop,
+            # normalise: bit-exact with the reference's per-frame torchvision pipelines on the CPU)
+            from .preprocess import preprocess_video
+            pre8, pre25, _ = preprocess_video(image, duration, frame_rate, device)
+            visual_feats, text_feats, audio_len_in_s = extract(pre8, pre25, prompt, negative_prompt)
+        elif image is not None:
             total_input_frames = image.shape[0]
             num_frames_to_process = int(duration * frame_rate)
             if num_frames_to_process > total_input_frames:   # hold the last frame (nodes.py:298-303)

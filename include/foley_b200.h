@@ -137,6 +137,23 @@ foley_status foley_denoise_solver(foley_engine* e, float* latents, const float* 
 foley_status foley_dac_decode(foley_engine* e, const float* z, int32_t batch, int32_t L, float* wav,
                               void* stream);
 
+/* ---- frame preprocessing for the condition encoders (nodes.py:293-317 + 184-196, utils.py:270-273) -------------
+ * image: DEVICE fp32 [n_frames, H, W, 3] in [0,1] (ComfyUI IMAGE).  frame_idx: T HOST indices into it — the 8 fps /
+ * 25 fps picks `torch.linspace(0, n-1, int(duration*fps)).long()` with the last frame held for short inputs.  Every
+ * picked frame is quantised like `(image*255).byte()`, resized to (resize_h, resize_w) with torchvision's uint8
+ * antialiased bicubic (ATen int16 fixed-point, horizontal pass first), cropped to the window [crop_top, +out_h) x
+ * [crop_left, +out_w), scaled by 1/255 and normalised with mean = std = 0.5.  out: DEVICE fp32 [T, 3, out_h, out_w].
+ * SigLIP2: resize 512x512, no crop.  Synchformer: short side to 224, centre crop 224.  Bit-exact with the reference's
+ * CPU path. */
+foley_status foley_preprocess_frames(const float* image, int32_t n_frames, int32_t H, int32_t W,
+                                     const int32_t* frame_idx, int32_t T, int32_t resize_h, int32_t resize_w,
+                                     int32_t crop_top, int32_t crop_left, int32_t out_h, int32_t out_w, float* out,
+                                     void* stream);
+/* Host-only: the fixed-point filter bank of one resize axis (xmin / xsize: out_size entries; w: out_size*max_interp
+ * int16, pass NULL to query max_interp first). */
+foley_status foley_resize_weights(int32_t in_size, int32_t out_size, int32_t* xmin, int32_t* xsize, int16_t* w,
+                                  int64_t w_cap, int32_t* max_interp, int32_t* precision);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* Number of kernel launches the engine issued (graph-replayed launches included) since create. */
 int64_t      foley_launch_count(const foley_engine* e);

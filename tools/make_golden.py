@@ -186,6 +186,47 @@ def gold_fp8_wrap(ns):
     print("wrote", path, len(wrapped), "of", len(linear_like), "modules wrapped", float(out.norm()))
 
 
+def gold_preprocess(ns):
+    """Frame preprocessing exactly as the reference's Sampler + Dependencies Loader do it (nodes.py:293-317, 184-196;
+    utils.py:270-273), executed with torch / torchvision here: hold-last-frame padding, (x*255).byte(), linspace picks at
+    8 / 25 fps, v2 Resize(bicubic, antialias) [+ CenterCrop] + ToDtype(scale) + Normalize on uint8 CHW views, per frame on
+    the CPU.  Full tensors for the small resize cases, SHA-256 digests for the two full pipelines (512x512 outputs are
+    too big for fixtures)."""
+    import hashlib
+    from torchvision.transforms import v2
+    siglip2_preprocess = v2.Compose([v2.Resize((512, 512), interpolation=v2.InterpolationMode.BICUBIC, antialias=True),
+                                     v2.ToDtype(torch.float32, scale=True), v2.Normalize(mean=[0.5] * 3, std=[0.5] * 3)])
+    syncformer_preprocess = v2.Compose([v2.Resize(224, interpolation=v2.InterpolationMode.BICUBIC, antialias=True),
+                                        v2.CenterCrop(224), v2.ToDtype(torch.float32, scale=True),
+                                        v2.Normalize(mean=[0.5] * 3, std=[0.5] * 3)])
+    out = {"cases": []}
+    for (N, H, W, duration, frame_rate, seed) in [(6, 90, 160, 1.0, 6.0, 7), (3, 250, 140, 1.0, 8.0, 8), (20, 64, 64, 2.0, 10.0, 9)]:
+        image = torch.rand(N, H, W, 3, generator=torch.Generator().manual_seed(seed))
+        n = int(duration * frame_rate)
+        image_slice = torch.cat((image, image[-1:].repeat(n - N, 1, 1, 1)), dim=0) if n > N else image[:n]
+        image_slice = (image_slice * 255.0).byte().permute(0, 3, 1, 2)
+        i8 = torch.linspace(0, n - 1, int(duration * 8)).long()
+        i25 = torch.linspace(0, n - 1, int(duration * 25)).long()
+        p8 = torch.stack([siglip2_preprocess(f) for f in image_slice.index_select(0, i8)])
+        p25 = torch.stack([syncformer_preprocess(f) for f in image_slice.index_select(0, i25)])
+        out["cases"].append({
+            "args": dict(N=N, H=H, W=W, duration=duration, frame_rate=frame_rate, seed=seed),
+            "idx8": i8, "idx25": i25,
+            "siglip2_sha256": hashlib.sha256(p8.numpy().tobytes()).hexdigest(), "siglip2_shape": tuple(p8.shape),
+            "sync_sha256": hashlib.sha256(p25.numpy().tobytes()).hexdigest(), "sync_shape": tuple(p25.shape),
+            "sync_frame0": p25[0].clone(),            # one full 3x224x224 frame per case (600 KB fp32 -> stored as fp16-exact? no: keep fp32)
+        })
+    small = []
+    for (H, W, oh, ow, seed) in [(90, 160, 45, 64, 1), (37, 53, 74, 106, 2), (64, 48, 64, 24, 3), (33, 200, 17, 31, 4)]:
+        img = torch.randint(0, 256, (H, W, 3), generator=torch.Generator().manual_seed(seed), dtype=torch.uint8).permute(2, 0, 1)
+        r = v2.functional.resize(img, [oh, ow], interpolation=v2.InterpolationMode.BICUBIC, antialias=True)
+        small.append({"args": dict(H=H, W=W, oh=oh, ow=ow, seed=seed), "out": r.contiguous().clone()})
+    out["resize_u8"] = small
+    path = os.path.join(GOLD, "preprocess.pt")
+    torch.save(out, path)
+    print("wrote", path, os.path.getsize(path) // 1024, "KB")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -205,6 +246,7 @@ def main():
         "denoise_kutta": lambda: gold_denoise(ns, "tiny_kutta4", 1.0, 8, 4.5, 1, True, "kutta-4"),
         "dac_full": lambda: gold_dac_full(ns),
         "fp8_wrap": lambda: gold_fp8_wrap(ns),
+        "preprocess": lambda: gold_preprocess(ns),
     }
     for k, fn in jobs.items():
         if a.only and a.only != k:
