@@ -80,6 +80,8 @@ foley_status Engine::create(const foley_config* c, int dev) {
         std::string err;
         if (!gemm_init_attributes(&err)) return fail(FOLEY_ERR_CUDA, err);
         FOLEY_CUDA_OK(cudaFuncSetAttribute(attention_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<4, 4>::SMEM));
+        FOLEY_CUDA_OK(cudaFuncSetAttribute(attention_kernel<8, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<8, 3, 2>::SMEM));
+        if (const char* e = getenv("FOLEY_ATT_KVSPLIT")) att_kv_split = atoi(e) != 0;
         FOLEY_CUDA_OK(cudaFuncSetAttribute(attention_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<8, 3>::SMEM));
     }
     triple.resize(NT);
@@ -690,6 +692,9 @@ foley_status Engine::step(cudaStream_t st) {
         if (ctas64 > 2LL * num_sms) {
             dim3 grid((Sq + 127) / 128, H, B2);
             FOLEY_CUDA_OK(launch_k(attention_kernel<8, 3>, grid, dim3(256), AttCfg<8, 3>::SMEM, st, a));
+        } else if (att_kv_split) {   // small grid: 8 warps = two key-tile groups over the same 64 queries (in-CTA split-KV)
+            dim3 grid((Sq + 63) / 64, H, B2);
+            FOLEY_CUDA_OK(launch_k(attention_kernel<8, 3, 2>, grid, dim3(256), AttCfg<8, 3, 2>::SMEM, st, a));
         } else {
             dim3 grid((Sq + 63) / 64, H, B2);
             FOLEY_CUDA_OK(launch_k(attention_kernel<4, 4>, grid, dim3(128), AttCfg<4, 4>::SMEM, st, a));

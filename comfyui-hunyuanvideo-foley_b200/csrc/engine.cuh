@@ -105,6 +105,7 @@ class Engine {
     cudaStream_t side_stream = nullptr;  // visual-stream branch of the step
     cudaStream_t mod_stream = nullptr;   // single-block modulation GEMM branch
     cudaEvent_t ev_mod = nullptr;
+    bool att_kv_split = true;            // small attention grids: in-CTA split-KV variant (FOLEY_ATT_KVSPLIT=0 disables)
     bool mod_on_branch = false;          // measured: no gain (the GEMM saturates the SMs either way)
     double plan_tkb128 = 0.30, plan_tkb256 = 0.38, plan_tfix = 5.0, plan_tsplit = 0.4;   // planner cost model (us)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

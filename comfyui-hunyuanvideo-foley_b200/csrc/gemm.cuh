@@ -223,6 +223,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
                 for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; ++k) {
                     // advance 32 bytes (= 2 x 16 B units) along K inside the swizzle atom
+                    // (Alternating the K-slices of a k-block between two TMEM accumulators changes nothing: the ~150-cycle
+                    // floor per tcgen05.mma, whatever N <= 256, is an issue-rate property, not an accumulator dependency.)
                     const uint32_t acc = (i | k) != 0;
                     if constexpr (kPair) {
                         if constexpr (kTF32) umma_tf32_pair(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
@@ -281,7 +283,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         const bool row_ok = r < g.rows;
         const long long row_off = static_cast<long long>(batch) * e.out_batch_stride +
                                   static_cast<long long>(r) * e.ldo;
-        if (e.mode != EPI_DAC && !(BN == 64 && e.mode == EPI_SWIGLU)) {   // (a 64-wide SwiGLU tile is half a store box)
+#ifndef FOLEY_SWIGLU_STAGED
+#define FOLEY_SWIGLU_STAGED 0
+#endif
+        // SwiGLU tiles write only 32 bytes per row and chunk: their direct stores were never the bottleneck, and the
+        // staged path costs them ~0.7 us of barriers (measured), so they keep storing from registers.
+        if (e.mode != EPI_DAC && (FOLEY_SWIGLU_STAGED ? !(BN == 64 && e.mode == EPI_SWIGLU) : e.mode != EPI_SWIGLU)) {
             // ---- DiT epilogues: the tile goes through shared memory (the idle operand ring) and leaves as TMA stores.
             // A thread owns one accumulator ROW, so direct stores made every warp instruction touch 32 different
             // lines (measured 2.5-6.5 us per tile, LSU-transaction bound); staged, the tile is written to global as

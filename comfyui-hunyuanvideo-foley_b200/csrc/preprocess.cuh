@@ -19,6 +19,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -86,30 +87,30 @@ __device__ __forceinline__ uint8_t quantize_u8(float v) {   // (image * 255.0).b
 __device__ __forceinline__ uint8_t clip_u8(int v) { return static_cast<uint8_t>(min(max(v, 0), 255)); }
 
 // pass 1 — grid (H, T), any block size.  image: fp32 [n,H,W,3]; tmp: uint8 [T,3,H,out_w].
+// The row is staged as one packed 0x00BBGGRR word per pixel: one shared-memory read per filter tap serves the three
+// channels (byte-planar staging made this kernel L1/LSU-bound at 93 % L1TEX throughput, 37 % of HBM: profiles/).
 __global__ void resize_rows_kernel(const float* __restrict__ image, const int* __restrict__ frame_idx, int H, int W,
                                    int out_w, const int* __restrict__ xmin, const int* __restrict__ xsize,
                                    const int16_t* __restrict__ wts, int max_interp, int precision, int col_lo, int col_hi,
                                    uint8_t* __restrict__ tmp) {
-    extern __shared__ uint8_t row_u8[];   // [3][W]
+    extern __shared__ uint32_t row_px[];   // [W]
     const int y = blockIdx.x, t = blockIdx.y;
     const float* src = image + (static_cast<long long>(frame_idx[t]) * H + y) * W * 3;
-    const int n_el = W * 3;
-    if ((n_el & 3) == 0) {   // 16-byte loads (rows are 16-byte aligned when W*3 is a multiple of 4): 4x fewer requests in flight per byte
+    if ((W & 3) == 0) {   // 4 pixels = 12 floats = three 16-byte loads per thread and step (rows are 16-byte aligned)
         const float4* src4 = reinterpret_cast<const float4*>(src);
-        for (int i4 = threadIdx.x; i4 < (n_el >> 2); i4 += blockDim.x) {
-            const float4 v = __ldg(src4 + i4);
-            const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = i4 * 4 + k, x = i / 3, c = i - x * 3;
-                row_u8[c * W + x] = quantize_u8(e[k]);
-            }
+        for (int p4 = threadIdx.x; p4 < (W >> 2); p4 += blockDim.x) {
+            const float4 a = __ldg(src4 + p4 * 3), b = __ldg(src4 + p4 * 3 + 1), c = __ldg(src4 + p4 * 3 + 2);
+            uint4 o;
+            o.x = quantize_u8(a.x) | (quantize_u8(a.y) << 8) | (quantize_u8(a.z) << 16);
+            o.y = quantize_u8(a.w) | (quantize_u8(b.x) << 8) | (quantize_u8(b.y) << 16);
+            o.z = quantize_u8(b.z) | (quantize_u8(b.w) << 8) | (quantize_u8(c.x) << 16);
+            o.w = quantize_u8(c.y) | (quantize_u8(c.z) << 8) | (quantize_u8(c.w) << 16);
+            reinterpret_cast<uint4*>(row_px)[p4] = o;
         }
     } else {
-        for (int i = threadIdx.x; i < n_el; i += blockDim.x) {   // coalesced over the interleaved RGB row
-            const int x = i / 3, c = i - x * 3;
-            row_u8[c * W + x] = quantize_u8(__ldg(src + i));
-        }
+        for (int x = threadIdx.x; x < W; x += blockDim.x)
+            row_px[x] = quantize_u8(__ldg(src + 3 * x)) | (quantize_u8(__ldg(src + 3 * x + 1)) << 8) |
+                        (quantize_u8(__ldg(src + 3 * x + 2)) << 16);
     }
     __syncthreads();
     const int round_add = 1 << (precision - 1);
@@ -119,9 +120,10 @@ __global__ void resize_rows_kernel(const float* __restrict__ image, const int* _
         int a0 = round_add, a1 = round_add, a2 = round_add;
         for (int j = 0; j < n; ++j) {
             const int wj = w[j];
-            a0 += wj * row_u8[x0 + j];
-            a1 += wj * row_u8[W + x0 + j];
-            a2 += wj * row_u8[2 * W + x0 + j];
+            const uint32_t px = row_px[x0 + j];
+            a0 += wj * static_cast<int>(px & 255u);
+            a1 += wj * static_cast<int>((px >> 8) & 255u);
+            a2 += wj * static_cast<int>(px >> 16);
         }
         const long long o = ((static_cast<long long>(t) * 3) * H + y) * out_w + xo;
         tmp[o] = clip_u8(a0 >> precision);
@@ -130,28 +132,52 @@ __global__ void resize_rows_kernel(const float* __restrict__ image, const int* _
     }
 }
 
-// pass 2 — one thread per output pixel.  tmp: uint8 [T,3,H,out_w] -> out fp32 [T,3,crop_h,crop_w] normalised.
+__device__ __forceinline__ float normalize_px(int u) {
+    // ToDtype(float32, scale=True): x.float() * (1/255); Normalize(0.5, 0.5): (x - 0.5) / 0.5   (all fp32, separately rounded)
+    const float f = __fmul_rn(static_cast<float>(u), 0.003921568859368563f);
+    return __fdiv_rn(__fsub_rn(f, 0.5f), 0.5f);
+}
+
+// pass 2 — one thread per FOUR horizontally adjacent output pixels (one 32-bit read of the uint8 intermediate per
+// tap and one 16-byte store).  tmp: uint8 [T,3,H,out_w] -> out fp32 [T,3,crop_h,crop_w] normalised.  quad = 1 needs
+// out_w, crop_left and crop_w to be multiples of 4 (the host picks); quad = 0 is the one-pixel-per-thread form.
 __global__ void resize_cols_normalize_kernel(const uint8_t* __restrict__ tmp, int T, int H, int out_w, int crop_top,
                                              int crop_left, int crop_h, int crop_w, const int* __restrict__ ymin,
                                              const int* __restrict__ ysize, const int16_t* __restrict__ wts,
-                                             int max_interp, int precision, float* __restrict__ out) {
+                                             int max_interp, int precision, int quad, float* __restrict__ out) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long total = static_cast<long long>(T) * 3 * crop_h * crop_w;
+    const int px_per = quad ? 4 : 1;
+    const int wq = crop_w / px_per;
+    const long long total = static_cast<long long>(T) * 3 * crop_h * wq;
     if (i >= total) return;
-    const int x = static_cast<int>(i % crop_w);
-    const int y = static_cast<int>((i / crop_w) % crop_h);
-    const long long tc = i / (static_cast<long long>(crop_w) * crop_h);
+    const int x = static_cast<int>(i % wq) * px_per;
+    const int y = static_cast<int>((i / wq) % crop_h);
+    const long long tc = i / (static_cast<long long>(wq) * crop_h);
     const uint8_t* plane = tmp + tc * H * out_w + (x + crop_left);
     const int yo = y + crop_top;
     // (equal sizes: ATen skips the pass; the bank then is the exact identity 2^p * delta, same bytes)
     const int y0 = ymin[yo], n = ysize[yo];
     const int16_t* w = wts + static_cast<long long>(yo) * max_interp;
-    int acc = 1 << (precision - 1);
-    for (int j = 0; j < n; ++j) acc += static_cast<int>(w[j]) * plane[static_cast<long long>(y0 + j) * out_w];
-    const int u = clip_u8(acc >> precision);
-    // ToDtype(float32, scale=True): x.float() * (1/255); Normalize(0.5, 0.5): (x - 0.5) / 0.5   (all fp32, separately rounded)
-    const float f = __fmul_rn(static_cast<float>(u), 0.003921568859368563f);
-    out[i] = __fdiv_rn(__fsub_rn(f, 0.5f), 0.5f);
+    const int round_add = 1 << (precision - 1);
+    float* dst = out + (tc * crop_h + y) * crop_w + x;
+    if (quad) {
+        int a0 = round_add, a1 = round_add, a2 = round_add, a3 = round_add;
+        const uint8_t* col = plane + static_cast<long long>(y0) * out_w;
+        for (int j = 0; j < n; ++j, col += out_w) {
+            const int wj = w[j];
+            const uint32_t p = *reinterpret_cast<const uint32_t*>(col);
+            a0 += wj * static_cast<int>(p & 255u);
+            a1 += wj * static_cast<int>((p >> 8) & 255u);
+            a2 += wj * static_cast<int>((p >> 16) & 255u);
+            a3 += wj * static_cast<int>(p >> 24);
+        }
+        *reinterpret_cast<float4*>(dst) = make_float4(normalize_px(clip_u8(a0 >> precision)), normalize_px(clip_u8(a1 >> precision)),
+                                                      normalize_px(clip_u8(a2 >> precision)), normalize_px(clip_u8(a3 >> precision)));
+    } else {
+        int acc = round_add;
+        for (int j = 0; j < n; ++j) acc += static_cast<int>(w[j]) * plane[static_cast<long long>(y0 + j) * out_w];
+        *dst = normalize_px(clip_u8(acc >> precision));
+    }
 }
 
 // Host driver.  frame_idx: T host indices into the image batch.  The resize target is (resize_h, resize_w); the
@@ -164,7 +190,7 @@ inline foley_status preprocess_frames(const float* image, int n_frames, int H, i
         return fail(FOLEY_ERR_INVALID, "preprocess_frames: empty shape");
     if (crop_top < 0 || crop_left < 0 || crop_top + out_h > resize_h || crop_left + out_w > resize_w)
         return fail(FOLEY_ERR_INVALID, "preprocess_frames: crop window outside the resized frame");
-    if (static_cast<long long>(W) * 3 > 96 * 1024) return fail(FOLEY_ERR_UNSUPPORTED, "preprocess_frames: frame wider than 32768 pixels");
+    if (W > 12 * 1024) return fail(FOLEY_ERR_UNSUPPORTED, "preprocess_frames: frame wider than 12288 pixels");
     for (int t = 0; t < T; ++t)
         if (frame_idx[t] < 0 || frame_idx[t] >= n_frames) return fail(FOLEY_ERR_INVALID, "preprocess_frames: frame index out of range");
     const ResizeBank bx = make_resize_bank(W, resize_w), by = make_resize_bank(H, resize_h);
@@ -181,26 +207,33 @@ inline foley_status preprocess_frames(const float* image, int n_frames, int H, i
         cudaFreeAsync(blk, st);
         return fail(FOLEY_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
     };
-    struct Up { size_t off; const void* src; size_t bytes; };
-    const Up ups[] = {{o_idx, frame_idx, sizeof(int) * T},
-                      {o_xmin, bx.xmin.data(), sizeof(int) * resize_w}, {o_xsize, bx.xsize.data(), sizeof(int) * resize_w},
-                      {o_ymin, by.xmin.data(), sizeof(int) * resize_h}, {o_ysize, by.xsize.data(), sizeof(int) * resize_h},
-                      {o_wx, bx.w.data(), sizeof(int16_t) * bx.w.size()}, {o_wy, by.w.data(), sizeof(int16_t) * by.w.size()}};
-    for (const Up& u : ups) {   // pageable sources: the call returns once they are staged, the vectors may die after it
-        cudaError_t e = cudaMemcpyAsync(blk + u.off, u.src, u.bytes, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) return bail(e, "preprocess_frames: table upload");
+    {   // all tables in ONE pageable upload (each such copy synchronises with the stream: seven of them cost more than the kernels)
+        std::vector<uint8_t> host(total - n_tmp);
+        auto put = [&](size_t off, const void* src, size_t bytes) { std::memcpy(host.data() + (off - n_tmp), src, bytes); };
+        put(o_idx, frame_idx, sizeof(int) * T);
+        put(o_xmin, bx.xmin.data(), sizeof(int) * resize_w);
+        put(o_xsize, bx.xsize.data(), sizeof(int) * resize_w);
+        put(o_ymin, by.xmin.data(), sizeof(int) * resize_h);
+        put(o_ysize, by.xsize.data(), sizeof(int) * resize_h);
+        put(o_wx, bx.w.data(), sizeof(int16_t) * bx.w.size());
+        put(o_wy, by.w.data(), sizeof(int16_t) * by.w.size());
+        cudaError_t e = cudaMemcpyAsync(blk + n_tmp, host.data(), host.size(), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return bail(e, "preprocess_frames: table upload");   // (staged before the call returns)
     }
     // pass 1 only for the columns the crop window keeps
-    resize_rows_kernel<<<dim3(H, T), 256, static_cast<size_t>(W) * 3, st>>>(
+    resize_rows_kernel<<<dim3(H, T), 256, static_cast<size_t>(W) * 4, st>>>(
         image, reinterpret_cast<const int*>(blk + o_idx), H, W, resize_w, reinterpret_cast<const int*>(blk + o_xmin),
         reinterpret_cast<const int*>(blk + o_xsize), reinterpret_cast<const int16_t*>(blk + o_wx), bx.max_interp, bx.precision,
         crop_left, crop_left + out_w, blk);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bail(e, "resize_rows_kernel");
-    const long long n_out = static_cast<long long>(T) * 3 * out_h * out_w;
-    resize_cols_normalize_kernel<<<static_cast<unsigned>((n_out + 255) / 256), 256, 0, st>>>(
+    // four pixels per thread when every 4-pixel group is 4-byte aligned in the intermediate and 16-byte aligned in the output
+    const int quad = (resize_w % 4 == 0 && crop_left % 4 == 0 && out_w % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+    const long long n_thr = static_cast<long long>(T) * 3 * out_h * (out_w / (quad ? 4 : 1));
+    resize_cols_normalize_kernel<<<static_cast<unsigned>((n_thr + 255) / 256), 256, 0, st>>>(
         blk, T, H, resize_w, crop_top, crop_left, out_h, out_w, reinterpret_cast<const int*>(blk + o_ymin),
-        reinterpret_cast<const int*>(blk + o_ysize), reinterpret_cast<const int16_t*>(blk + o_wy), by.max_interp, by.precision, out);
+        reinterpret_cast<const int*>(blk + o_ysize), reinterpret_cast<const int16_t*>(blk + o_wy), by.max_interp, by.precision,
+        quad, out);
     e = cudaGetLastError();
     if (e != cudaSuccess) return bail(e, "resize_cols_normalize_kernel");
     FOLEY_CUDA_OK(cudaFreeAsync(blk, st));
