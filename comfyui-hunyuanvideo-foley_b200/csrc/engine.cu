@@ -73,6 +73,7 @@ foley_status Engine::create(const foley_config* c, int dev) {
     FOLEY_CUDA_OK(cudaStreamCreateWithFlags(&mod_stream, cudaStreamNonBlocking));
     FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_mod, cudaEventDisableTiming));
     if (const char* e = getenv("FOLEY_MOD_BRANCH")) mod_on_branch = atoi(e) != 0;
+    if (const char* e = getenv("FOLEY_QKV_SPLIT")) qkv_split = atoi(e) != 0;
     if (const char* e = getenv("FOLEY_PLAN")) sscanf(e, "%lf,%lf,%lf,%lf", &plan_tkb128, &plan_tkb256, &plan_tfix, &plan_tsplit);
     FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -403,15 +404,16 @@ foley_status Engine::alloc_plan(int B, int U, int L, int Lv, int S, int T) {
     return FOLEY_OK;
 }
 
-// Tile-shape / K-split planner.  The kernel is bound by the TMA round trip per k-block (profiles/r01_gemm_micro.txt:
-// ~0.30 us per k-block with 128-wide tiles, ~0.38 us with 256-wide ones, ~5 us of launch + prologue + epilogue per
-// CTA wave), so the cost model is  waves x (k-blocks per CTA x t_kb + t_fixed)  and the planner picks the
-// (tile width, split) pair that minimises it.
-void Engine::plan_gemm(int rows, int batch, int n, int kblocks, bool can_split, int* bn_out, int* splits_out) const {
+// Tile-shape / K-split planner.  Measured (profiles/r01_experiments.md): ~0.35 us per 64-deep k-block for 64-, 128- and
+// 256-wide tiles alike (the MMA issue rate, not TMA, sets it), ~5 us of launch + prologue + epilogue per CTA wave, so
+// the cost model is  waves x (k-blocks per CTA x t_kb + t_fixed)  and the planner picks the (tile width, split) pair
+// that minimises it.
+void Engine::plan_gemm(int rows, int batch, int n, int kblocks, bool can_split, int* bn_out, int* splits_out, int split_cap) const {
     const long long m_tiles = static_cast<long long>((rows + 127) / 128) * batch;
     double best = 1e30;
     int best_bn = 128, best_s = 1;
-    const int smax = can_split ? std::min(max_splits, max_splits_used) : 1;
+    int smax = can_split ? std::min(max_splits, max_splits_used) : 1;
+    if (split_cap > 0) smax = std::min(smax, split_cap);
     for (int bn : {128, 256}) {
         const long long n_tiles = (n + bn - 1) / bn;
         const double t_kb = bn == 128 ? plan_tkb128 : plan_tkb256;
@@ -747,6 +749,26 @@ foley_status Engine::step(cudaStream_t st) {
         ++launches;
         return FOLEY_OK;
     };
+    // Audio-stream QKV / cross-Q projections: per-k-block cost does not depend on the tile width (§3.1), so the fastest
+    // shape is the widest tile with K split until the SMs are full; the q/k-norm + RoPE kernel that consumes the result
+    // sums the fp32 partials (+ bias, bf16 rounding) itself.  Returns the args the consumer needs in `q`.
+    auto qkv_gemm = [&](const LinearW& W, int n_cols, QkvArgs* q) -> foley_status {
+        int bn = 128, splits = 1;
+        plan_gemm(L, B2, n_cols, W.k / 64, qkv_split, &bn, &splits, max_splits * C / n_cols);   // partials share part_a
+        if (splits > 1) {
+            GemmEpi e;
+            e.mode = EPI_F32; e.out = part_a; e.ldo = n_cols;
+            e.out_batch_stride = static_cast<long long>(L) * n_cols;
+            e.split_stride = static_cast<long long>(L) * B2 * n_cols;
+            ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, W, 0, n_cols, e, splits, bn));
+            q->partials = part_a; q->splits = splits; q->split_stride = e.split_stride; q->bias = W.b; q->src = nullptr;
+        } else {
+            ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, W, 0, n_cols, bf(qkv_a, n_cols, W.b, 0), 1, bn));
+            q->src = qkv_a;
+        }
+        q->src_ld = n_cols;
+        return FOLEY_OK;
+    };
     const int RV = B2 * Lv;   // visual rows, flattened (no token conv on this stream, so samples need no halo)
     // ---- embed: audio0 = audio_embedder(x) + a_sync (fp32), v_cond0; LN+modulate for block 0
     {
@@ -764,11 +786,13 @@ foley_status Engine::step(cudaStream_t st) {
     for (int i = 0; i < ((debug_skip >> 9) & 1 ? 0 : NT); ++i) {
         const TripleW& w = triple[i];
         // -- joint self attention
-        ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.qkv[0], 0, 3 * C, bf(qkv_a, C3, w.qkv[0].b, 0), 1, pick_bn(L, B2, 3 * C, C / 64)));
+        QkvArgs qa_joint;
+        ST_OK(qkv_gemm(w.qkv[0], 3 * C, &qa_joint));
         ST_OK(gemm(sv, h_v, RV, 1, C, 0, w.qkv[1], 0, 3 * C, bf(qkv_v, C3, w.qkv[1].b, 0), 1, 64));
         for (int s = 0; s < 2; ++s) {
-            QkvArgs q;
-            q.src = s == 0 ? qkv_a : qkv_v; q.src_ld = 3 * C; q.n_parts = 3; q.H = H; q.L = s == 0 ? L : Lv;
+            QkvArgs q = s == 0 ? qa_joint : QkvArgs();
+            if (s == 1) { q.src = qkv_v; q.src_ld = 3 * C; }
+            q.n_parts = 3; q.H = H; q.L = s == 0 ? L : Lv;
             q.rows_total = B2 * q.L; q.norm_kind = 0; q.eps = 1e-6f;
             q.cos = s == 0 ? rope_av_a_cos : rope_av_v_cos; q.sin = s == 0 ? rope_av_a_sin : rope_av_v_sin;
             bf16* dsts[3] = {Qj, Kj, Vj};
@@ -793,11 +817,13 @@ foley_status Engine::step(cudaStream_t st) {
             ST_OK(proj_combine(sv, attn_out, Lv, B2, C, jb, w.self_proj[1], part_v, cv));
         }
         // -- cross attention to text
-        ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.cross_q[0], 0, C, bf(qkv_a, C, w.cross_q[0].b, 0), 1, 64));
+        QkvArgs qa_cross;
+        ST_OK(qkv_gemm(w.cross_q[0], C, &qa_cross));
         ST_OK(gemm(sv, h_v, RV, 1, C, 0, w.cross_q[1], 0, C, bf(qkv_v, C, w.cross_q[1].b, 0), 1, 64));
         for (int s = 0; s < 2; ++s) {
-            QkvArgs q;
-            q.src = s == 0 ? qkv_a : qkv_v; q.src_ld = C; q.n_parts = 1; q.H = H; q.L = s == 0 ? L : Lv;
+            QkvArgs q = s == 0 ? qa_cross : QkvArgs();
+            if (s == 1) { q.src = qkv_v; q.src_ld = C; }
+            q.n_parts = 1; q.H = H; q.L = s == 0 ? L : Lv;
             q.rows_total = B2 * q.L; q.norm_kind = 0; q.eps = 1e-6f; q.cos = rope_plain_cos; q.sin = rope_plain_sin;
             q.part[0].dst = Qj; q.part[0].dst_batch_stride = jb; q.part[0].dst_head_stride = jh;
             q.part[0].seq_offset = s == 0 ? Lv : 0; q.part[0].norm_w = w.cross_q_norm[s]; q.part[0].src_col = 0;
@@ -842,10 +868,10 @@ foley_status Engine::step(cudaStream_t st) {
     for (int j = 0; j < ((debug_skip >> 10) & 1 ? 0 : NS); ++j) {
         const SingleW& w = single[j];
         skip_gemm_once = (debug_skip >> 5) & 1;
-        ST_OK(gemm(st, h_a, L, B2, C, sb, w.qkv, 0, 3 * C, bf(qkv_a, C3, w.qkv.b, 0), 1, pick_bn(L, B2, 3 * C, C / 64)));
         {
             QkvArgs q;
-            q.src = qkv_a; q.src_ld = 3 * C; q.n_parts = 3; q.H = H; q.L = L; q.rows_total = B2 * L;
+            ST_OK(qkv_gemm(w.qkv, 3 * C, &q));
+            q.n_parts = 3; q.H = H; q.L = L; q.rows_total = B2 * L;
             q.norm_kind = 1; q.eps = cfg.single_rms_eps; q.cos = rope_plain_cos; q.sin = rope_plain_sin;
             bf16* dsts[3] = {Qj, Kj, Vj};
             const bf16* norms[3] = {w.q_norm, w.k_norm, nullptr};

@@ -105,9 +105,12 @@ class Engine {
     cudaStream_t side_stream = nullptr;  // visual-stream branch of the step
     cudaStream_t mod_stream = nullptr;   // single-block modulation GEMM branch
     cudaEvent_t ev_mod = nullptr;
+    bool qkv_split = true;               // audio QKV / cross-Q GEMMs may split K (partials summed by the q/k-norm kernel)
     bool att_kv_split = true;            // small attention grids: in-CTA split-KV variant (FOLEY_ATT_KVSPLIT=0 disables)
     bool mod_on_branch = false;          // measured: no gain (the GEMM saturates the SMs either way)
-    double plan_tkb128 = 0.30, plan_tkb256 = 0.38, plan_tfix = 5.0, plan_tsplit = 0.4;   // planner cost model (us)
+    // planner cost model (us): a k-block costs the same for every tile width (one tcgen05.mma ~150 cycles whatever N), so
+    // wide tiles + more K-splits win whenever they fit the SMs (measured: tools/gemm_micro.py --dbg 4, FOLEY_PLAN sweeps)
+    double plan_tkb128 = 0.35, plan_tkb256 = 0.36, plan_tfix = 5.0, plan_tsplit = 0.4;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t own_stream = nullptr;   // blocking stream used when the caller passes NULL (legacy stream cannot be captured)
     // scratch of set_conditions / prepare_timesteps (plan-owned)
@@ -152,7 +155,7 @@ class Engine {
     template <typename T> foley_status palloc(T** p, size_t count);
     int pick_splits(int rows, int batch, int n, int kblocks, int bn) const;
     int pick_bn(int rows, int batch, int n, int kblocks) const;
-    void plan_gemm(int rows, int batch, int n, int kblocks, bool can_split, int* bn_out, int* splits_out) const;
+    void plan_gemm(int rows, int batch, int n, int kblocks, bool can_split, int* bn_out, int* splits_out, int split_cap = 0) const;
     foley_status proj_combine(cudaStream_t st, const bf16* A, int rows, int batch, long long lda, long long a_bs,
                               const LinearW& W, float* partials, CombineArgs ca);
 };

@@ -189,6 +189,12 @@ struct QkvArgs {
     int rows_total = 0;
     int norm_kind = 0;
     float eps = 1e-6f;
+    // split-K producer: when `partials` is set the source row is bf16r(sum_s partials[s][row][col] + bias[col]) — what
+    // the bf16 GEMM epilogue would have written — and `src` is not read
+    const float* partials = nullptr;     // [splits][rows_total][src_ld] fp32
+    int splits = 0;
+    long long split_stride = 0;
+    const __nv_bfloat16* bias = nullptr; // [src_ld] or null
     const float* cos = nullptr;          // [P][128] fp32 tables
     const float* sin = nullptr;
     const int* pos = nullptr;            // [L] table row of token l; nullptr -> l
@@ -213,11 +219,25 @@ __global__ void __launch_bounds__(128) qk_norm_rope_kernel(const QkvArgs a) {
         c = *reinterpret_cast<const float4*>(a.cos + static_cast<long long>(prow) * 128 + lane * 4);
         s = *reinterpret_cast<const float4*>(a.sin + static_cast<long long>(prow) * 128 + lane * 4);
     }
+    float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+    const int col = p.src_col + head * 128 + lane * 4;
+    if (active && a.partials && a.bias) load_bf16x4(a.bias + col, bias4);   // static too
     pdl_wait();
     pdl_trigger();
     if (!active) return;
     float v[4];
-    load_bf16x4(a.src + static_cast<long long>(row) * a.src_ld + p.src_col + head * 128 + lane * 4, v);
+    if (a.partials) {
+        const float* pr = a.partials + static_cast<long long>(row) * a.src_ld + col;
+        float4 acc = *reinterpret_cast<const float4*>(pr);
+        for (int sp = 1; sp < a.splits; ++sp) {
+            const float4 q = *reinterpret_cast<const float4*>(pr + sp * a.split_stride);
+            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+        }
+        v[0] = bf16_round(acc.x + bias4[0]); v[1] = bf16_round(acc.y + bias4[1]);
+        v[2] = bf16_round(acc.z + bias4[2]); v[3] = bf16_round(acc.w + bias4[3]);
+    } else {
+        load_bf16x4(a.src + static_cast<long long>(row) * a.src_ld + col, v);
+    }
     if (p.norm_w) {
         const float ss = warp_sum(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
         const float rstd = rsqrtf(ss * (1.0f / 128.0f) + a.eps);
