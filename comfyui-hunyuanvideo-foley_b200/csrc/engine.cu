@@ -378,7 +378,7 @@ foley_status Engine::alloc_plan(int B, int U, int L, int Lv, int S, int T) {
     ST_OK(palloc(&audio, B2 * L * C));
     ST_OK(palloc(&vcond, B2 * Lv * C));
     ST_OK(palloc(&part_a, static_cast<size_t>(max_splits) * B2 * L * C));
-    ST_OK(palloc(&part_v, static_cast<size_t>(max_splits) * B2 * Lv * C));
+    ST_OK(palloc(&part_v, static_cast<size_t>(max_splits) * B2 * Lv * 3 * C));   // also the visual QKV partials (3C wide)
     ST_OK(palloc(&lat_dev, static_cast<size_t>(B) * LAT * L));
     {
         const size_t US = static_cast<size_t>(U) * S, UT = static_cast<size_t>(U) * T, ULv = static_cast<size_t>(U) * Lv;
@@ -658,7 +658,6 @@ foley_status Engine::prepare_timesteps(const float* t_host, int n_t, bool per_sa
 foley_status Engine::step(cudaStream_t st) {
     const Plan& p = plan;
     const int B2 = p.B2, L = p.L, Lv = p.Lv, T = p.T, Sj = L + Lv, G = cur_G;
-    const long long C3 = 3LL * C;
     RowMap rm_a{grp_of_sample, trow_of_grp, cond_of_grp, L};
     RowMap rm_v{grp_of_sample, trow_of_grp, cond_of_grp, Lv};
     const long long mt_stride = static_cast<long long>(NT) * 18 * C;
@@ -752,19 +751,21 @@ foley_status Engine::step(cudaStream_t st) {
     // Audio-stream QKV / cross-Q projections: per-k-block cost does not depend on the tile width (§3.1), so the fastest
     // shape is the widest tile with K split until the SMs are full; the q/k-norm + RoPE kernel that consumes the result
     // sums the fp32 partials (+ bias, bf16 rounding) itself.  Returns the args the consumer needs in `q`.
-    auto qkv_gemm = [&](const LinearW& W, int n_cols, QkvArgs* q) -> foley_status {
+    auto qkv_gemm = [&](cudaStream_t s_, const bf16* A, int rows, int batch, const LinearW& W, int n_cols, float* partials,
+                        int part_cols, bf16* out_bf16, QkvArgs* q) -> foley_status {
         int bn = 128, splits = 1;
-        plan_gemm(L, B2, n_cols, W.k / 64, qkv_split, &bn, &splits, max_splits * C / n_cols);   // partials share part_a
+        plan_gemm(rows, batch, n_cols, W.k / 64, qkv_split, &bn, &splits, max_splits * part_cols / n_cols);   // workspace cap
+        const long long a_bs = static_cast<long long>(rows) * C;
         if (splits > 1) {
             GemmEpi e;
-            e.mode = EPI_F32; e.out = part_a; e.ldo = n_cols;
-            e.out_batch_stride = static_cast<long long>(L) * n_cols;
-            e.split_stride = static_cast<long long>(L) * B2 * n_cols;
-            ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, W, 0, n_cols, e, splits, bn));
-            q->partials = part_a; q->splits = splits; q->split_stride = e.split_stride; q->bias = W.b; q->src = nullptr;
+            e.mode = EPI_F32; e.out = partials; e.ldo = n_cols;
+            e.out_batch_stride = static_cast<long long>(rows) * n_cols;
+            e.split_stride = static_cast<long long>(rows) * batch * n_cols;
+            ST_OK(gemm(s_, A, rows, batch, C, a_bs, W, 0, n_cols, e, splits, bn));
+            q->partials = partials; q->splits = splits; q->split_stride = e.split_stride; q->bias = W.b; q->src = nullptr;
         } else {
-            ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, W, 0, n_cols, bf(qkv_a, n_cols, W.b, 0), 1, bn));
-            q->src = qkv_a;
+            ST_OK(gemm(s_, A, rows, batch, C, a_bs, W, 0, n_cols, bf(out_bf16, n_cols, W.b, 0), 1, bn));
+            q->src = out_bf16;
         }
         q->src_ld = n_cols;
         return FOLEY_OK;
@@ -786,12 +787,11 @@ foley_status Engine::step(cudaStream_t st) {
     for (int i = 0; i < ((debug_skip >> 9) & 1 ? 0 : NT); ++i) {
         const TripleW& w = triple[i];
         // -- joint self attention
-        QkvArgs qa_joint;
-        ST_OK(qkv_gemm(w.qkv[0], 3 * C, &qa_joint));
-        ST_OK(gemm(sv, h_v, RV, 1, C, 0, w.qkv[1], 0, 3 * C, bf(qkv_v, C3, w.qkv[1].b, 0), 1, 64));
+        QkvArgs qa_joint, qv_joint;
+        ST_OK(qkv_gemm(st, h_a, L, B2, w.qkv[0], 3 * C, part_a, C, qkv_a, &qa_joint));
+        ST_OK(qkv_gemm(sv, h_v, RV, 1, w.qkv[1], 3 * C, part_v, 3 * C, qkv_v, &qv_joint));
         for (int s = 0; s < 2; ++s) {
-            QkvArgs q = s == 0 ? qa_joint : QkvArgs();
-            if (s == 1) { q.src = qkv_v; q.src_ld = 3 * C; }
+            QkvArgs q = s == 0 ? qa_joint : qv_joint;
             q.n_parts = 3; q.H = H; q.L = s == 0 ? L : Lv;
             q.rows_total = B2 * q.L; q.norm_kind = 0; q.eps = 1e-6f;
             q.cos = s == 0 ? rope_av_a_cos : rope_av_v_cos; q.sin = s == 0 ? rope_av_a_sin : rope_av_v_sin;
@@ -817,12 +817,11 @@ foley_status Engine::step(cudaStream_t st) {
             ST_OK(proj_combine(sv, attn_out, Lv, B2, C, jb, w.self_proj[1], part_v, cv));
         }
         // -- cross attention to text
-        QkvArgs qa_cross;
-        ST_OK(qkv_gemm(w.cross_q[0], C, &qa_cross));
-        ST_OK(gemm(sv, h_v, RV, 1, C, 0, w.cross_q[1], 0, C, bf(qkv_v, C, w.cross_q[1].b, 0), 1, 64));
+        QkvArgs qa_cross, qv_cross;
+        ST_OK(qkv_gemm(st, h_a, L, B2, w.cross_q[0], C, part_a, C, qkv_a, &qa_cross));
+        ST_OK(qkv_gemm(sv, h_v, RV, 1, w.cross_q[1], C, part_v, 3 * C, qkv_v, &qv_cross));
         for (int s = 0; s < 2; ++s) {
-            QkvArgs q = s == 0 ? qa_cross : QkvArgs();
-            if (s == 1) { q.src = qkv_v; q.src_ld = C; }
+            QkvArgs q = s == 0 ? qa_cross : qv_cross;
             q.n_parts = 1; q.H = H; q.L = s == 0 ? L : Lv;
             q.rows_total = B2 * q.L; q.norm_kind = 0; q.eps = 1e-6f; q.cos = rope_plain_cos; q.sin = rope_plain_sin;
             q.part[0].dst = Qj; q.part[0].dst_batch_stride = jb; q.part[0].dst_head_stride = jh;
@@ -870,7 +869,7 @@ foley_status Engine::step(cudaStream_t st) {
         skip_gemm_once = (debug_skip >> 5) & 1;
         {
             QkvArgs q;
-            ST_OK(qkv_gemm(w.qkv, 3 * C, &q));
+            ST_OK(qkv_gemm(st, h_a, L, B2, w.qkv, 3 * C, part_a, C, qkv_a, &q));
             q.n_parts = 3; q.H = H; q.L = L; q.rows_total = B2 * L;
             q.norm_kind = 1; q.eps = cfg.single_rms_eps; q.cos = rope_plain_cos; q.sin = rope_plain_sin;
             bf16* dsts[3] = {Qj, Kj, Vj};
