@@ -16,6 +16,10 @@
 #pragma once
 #include "ptx.cuh"
 
+#ifndef FOLEY_EPI_WARPS_BF16
+#define FOLEY_EPI_WARPS_BF16 16
+#endif
+
 namespace foley {
 
 enum EpiMode : int {
@@ -72,7 +76,13 @@ struct GemmCfg {
     static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 3 * 256 * 4 /*epilogue params*/;
-    static constexpr int THREADS = 352;   // weight-TMA warp, MMA warp, 8 epilogue warps, activation-TMA warp
+    // weight-TMA warp, MMA warp, epilogue warps, activation-TMA warp.  The bf16 (DiT) kernels run 16 epilogue warps —
+    // their epilogues are issue-bound math (SiLU / GELU / SwiGLU, bf16 rounding) on 128 x BN accumulators, and four
+    // warps per scheduler hide what two cannot; the tf32 (DAC) kernels keep 8: their epilogue needs > 100 registers.
+    static constexpr int EPI_WARPS = FOLEY_EPI_WARPS_BF16 == 16 && !kTF32 ? 16 : 8;
+    static constexpr int EPI_GROUPS = EPI_WARPS / 4;          // warps per TMEM lane quarter = interleaved column-chunk sets
+    static constexpr int A_WARP = 2 + EPI_WARPS;              // warp id of the activation producer
+    static constexpr int THREADS = 32 * (3 + EPI_WARPS);
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -85,7 +95,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 }
 
 template <int BN, bool kTF32, bool kPair = false>
-__global__ void __launch_bounds__(352, 1)
+__global__ void __launch_bounds__((GemmCfg<BN, kTF32, kPair>::THREADS), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const __grid_constant__ CUtensorMap tm_c, const GemmArgs g) {
     using Cfg = GemmCfg<BN, kTF32, kPair>;
@@ -170,7 +180,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == Cfg::A_WARP) {
         // ------------------------------------------------------------- TMA producer: activation tiles
         if (lane == 0) {
             int tap = kb_begin / g.kb_per_tap;
@@ -251,13 +261,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // ------------------------------------------------------------- epilogue warps (2..9)
         // Two warps per TMEM lane quarter; each takes every other 32-column chunk.  Per-column parameters (bias,
         // snake alpha and 1/alpha) are staged in shared memory while the mainloop runs.
+        constexpr int NG = Cfg::EPI_GROUPS;  // column-chunk sets: chunk c0 = half*32 + it*32*NG belongs to set `half`
+        constexpr int EPI_THREADS = 32 * Cfg::EPI_WARPS;
+        constexpr int NIT = (BN + 32 * NG - 1) / (32 * NG);
         const int q = warp & 3;              // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;    // which interleaved set of column chunks
         const int r = m0 + q * 32 + lane;    // output row within the sample
         const GemmEpi& e = g.epi;
         {
             const int et = threadIdx.x - 64;
-            for (int c = et; c < BN; c += 256) {
+            for (int c = et; c < BN; c += EPI_THREADS) {
                 const int col = n0 + c;
                 float bv = 0.f, al = 0.f, ial = 0.f;
                 if (col < g.n) {
@@ -271,7 +284,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 }
                 epi_f[c] = bv; epi_f[256 + c] = al; epi_f[512 + c] = ial;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         }
         pdl_wait();                          // outputs may alias buffers the predecessor still reads
         // (Parking these warps in a hardware barrier until warp 1 has seen the accumulator barrier, instead of letting
@@ -302,7 +315,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const uint32_t stage_base = smem_u32(smem);
             const bool live = acc_ok && (g.dbg_stop & 7) == 0 && num_kb > 0;
             int boxes_issued = 0;
-            constexpr int NIT = BN / 64;
             // One accumulator chunk (32 columns of this thread's row) -> fused math -> swizzled staging row.
             auto emit = [&](const uint32_t (&v)[32], int c0) {
                 const float* pb = epi_f + c0;
@@ -350,18 +362,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32;
 #pragma unroll 1   // (fully unrolled, the three fused epilogues x four chunks ran 40 % slower: measured)
             for (int it = 0; it < NIT; ++it) {
-                const int c0 = half * 32 + it * 64;
-                if (live && n0 + c0 < g.n) {
+                const int c0 = half * 32 + it * 32 * NG;
+                if (live && c0 < BN && n0 + c0 < g.n) {
                     uint32_t v[32];
-                    tmem_ld_32x32(t_row + it * 64, v);
+                    tmem_ld_32x32(t_row + it * 32 * NG, v);
                     tmem_ld_wait();
                     emit(v, c0);
                 }
-                {   // every 64-column group leaves as soon as all eight warps have written it
+                {   // every column group leaves as soon as all epilogue warps have written it
                     fence_proxy_async();                          // generic-proxy smem writes -> visible to the TMA store
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                     if (threadIdx.x == 64 && live) {
-                        const int boxes_done = ((it + 1) * 64 * bpc) >> 7;
+                        const int cols_done = (it + 1) * 32 * NG < BN ? (it + 1) * 32 * NG : BN;
+                        const int boxes_done = (cols_done * bpc) >> 7;
                         for (; boxes_issued < boxes_done; ++boxes_issued) {
                             const int col_elem = (n0 * bpc + boxes_issued * 128) / esz;
                             if (col_elem < n_out)
@@ -374,34 +387,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             if (threadIdx.x == 64) tma_store_wait_read();         // the staging memory must outlive the reads
         } else
 #pragma unroll 1
-        for (int c0 = half * 32; c0 < BN && acc_ok && (g.dbg_stop & 7) == 0; c0 += 64) {
+        for (int c0 = half * 32; c0 < BN && acc_ok && (g.dbg_stop & 7) == 0; c0 += 32 * NG) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
             tmem_ld_wait();
             const int col = n0 + c0;
             if (!row_ok || col >= g.n || num_kb <= 0) continue;
             const float* pb = epi_f + c0;
-            if (e.mode == EPI_BF16) {
-                __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out) + row_off + col;
-                uint32_t packed[16];
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float a0 = __uint_as_float(v[j]) + pb[j], a1 = __uint_as_float(v[j + 1]) + pb[j + 1];
-                    if (e.act == ACT_SILU) {
-                        a0 = bf16_round(a0); a1 = bf16_round(a1);
-                        a0 = __fdividef(a0, 1.0f + __expf(-a0));
-                        a1 = __fdividef(a1, 1.0f + __expf(-a1));
-                    } else if (e.act != ACT_NONE) {
-                        a0 = apply_act(bf16_round(a0), e.act);
-                        a1 = apply_act(bf16_round(a1), e.act);
-                    }
-                    packed[j >> 1] = pack_bf16x2(a0, a1);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(out);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-            } else if (e.mode == EPI_SWIGLU) {
+            if (e.mode == EPI_SWIGLU) {
                 __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out) + row_off + (col >> 1);
                 uint32_t packed[8];
 #pragma unroll
@@ -415,15 +408,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 uint4* dst = reinterpret_cast<uint4*>(out);
                 dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                 dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-            } else if (e.mode == EPI_F32) {
-                float* out = reinterpret_cast<float*>(e.out) + static_cast<long long>(split) * e.split_stride +
-                             row_off + col;
-                float4* dst = reinterpret_cast<float4*>(out);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            } else {  // EPI_DAC
+            } else if constexpr (kTF32) {  // EPI_DAC (fp32 / tf32 decoder convolutions only)
                 const long long flat0 = static_cast<long long>(r) * e.ldo + col;
                 const bool windowed = e.flat_hi > e.flat_lo;
                 float* out = e.out ? reinterpret_cast<float*>(e.out) + row_off + col : nullptr;

@@ -253,6 +253,7 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
     const int bk = tf32 ? 32 : 64;
     if (L.a.k % bk != 0) { if (err) *err = "GEMM K must be a multiple of the 128-byte k-block"; return false; }
     if (L.n % 16 != 0) { if (err) *err = "GEMM N must be a multiple of 16"; return false; }
+    if (L.epi.mode == EPI_DAC && !tf32) { if (err) *err = "the DAC epilogue exists for fp32 / tf32 operands only"; return false; }
     const long long out_rows_c = L.out_rows > 0 ? L.out_rows : L.a.rows;
     const long long mt = ((out_rows_c + 127) / 128) * (L.a.batch > 0 ? L.a.batch : 1);
     const long long nt = (L.n + L.bn - 1) / L.bn;
