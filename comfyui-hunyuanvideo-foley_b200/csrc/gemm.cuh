@@ -17,7 +17,7 @@
 #include "ptx.cuh"
 
 #ifndef FOLEY_EPI_WARPS_BF16
-#define FOLEY_EPI_WARPS_BF16 16
+#define FOLEY_EPI_WARPS_BF16 8    // 16 measured: fc1 (GELU) 14.5 -> 13.7 us, but w2 / w1|w3 0.3 us slower; step 4.14 -> 4.17 ms
 #endif
 
 namespace foley {
@@ -76,9 +76,9 @@ struct GemmCfg {
     static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 3 * 256 * 4 /*epilogue params*/;
-    // weight-TMA warp, MMA warp, epilogue warps, activation-TMA warp.  The bf16 (DiT) kernels run 16 epilogue warps —
-    // their epilogues are issue-bound math (SiLU / GELU / SwiGLU, bf16 rounding) on 128 x BN accumulators, and four
-    // warps per scheduler hide what two cannot; the tf32 (DAC) kernels keep 8: their epilogue needs > 100 registers.
+    // weight-TMA warp, MMA warp, epilogue warps, activation-TMA warp.  8 epilogue warps (two per TMEM lane quarter);
+    // the bf16 (DiT) kernels can be built with 16 (-DFOLEY_EPI_WARPS_BF16=16: no net gain, see above), the tf32 (DAC)
+    // kernels always keep 8: their epilogue needs > 100 registers.
     static constexpr int EPI_WARPS = FOLEY_EPI_WARPS_BF16 == 16 && !kTF32 ? 16 : 8;
     static constexpr int EPI_GROUPS = EPI_WARPS / 4;          // warps per TMEM lane quarter = interleaved column-chunk sets
     static constexpr int A_WARP = 2 + EPI_WARPS;              // warp id of the activation producer
