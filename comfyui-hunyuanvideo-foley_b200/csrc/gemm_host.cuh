@@ -4,10 +4,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
 #include <string>
 
 #include "gemm.cuh"
+#include "gemm_persistent.cuh"
 
 namespace foley {
 
@@ -232,6 +234,7 @@ inline bool gemm_init_attributes(std::string* err) {
     auto set = [&](auto kern, int bytes) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     };
+    set(gemm_persistent_kernel, PersistCfg::SMEM_BYTES);
     set(gemm_tcgen05_kernel<64, false>, GemmCfg<64, false>::SMEM_BYTES);
     set(gemm_tcgen05_kernel<128, false>, GemmCfg<128, false>::SMEM_BYTES);
     set(gemm_tcgen05_kernel<256, false>, GemmCfg<256, false>::SMEM_BYTES);
@@ -293,6 +296,55 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
     dim3 grid(static_cast<unsigned>(m_tiles * (L.a.batch > 0 ? L.a.batch : 1)),
               static_cast<unsigned>(((nt + cy - 1) / cy) * cy), static_cast<unsigned>(args.splits));
     cudaError_t e = cudaSuccess;
+    // Grids of more than ~1.5 waves of 256-wide bf16 tiles go to the persistent kernel (epilogue of tile j under the
+    // mainloop of tile j+1, one prologue per SM).  FOLEY_GEMM_PERSIST=0 disables.
+    {
+        static int persist = -1, sms = 0;
+        if (persist < 0) {
+            const char* ev = getenv("FOLEY_GEMM_PERSIST");
+            persist = ev ? atoi(ev) : 1;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const long long tiles = static_cast<long long>(grid.x) * grid.y * grid.z;
+        // (fp32 K-split partials stay on the one-tile kernel unless FOLEY_GEMM_PERSIST=2: their 128 KB tile needs two
+        // staging rounds here and measured 3 % slower; bf16 / SwiGLU outputs measured 5-25 % faster)
+        const bool mode_ok = L.epi.mode == EPI_BF16 || L.epi.mode == EPI_SWIGLU || (L.epi.mode == EPI_F32 && persist >= 2);
+        if (persist && mode_ok && !tf32 && L.bn == 256 && !pair && (L.dbg_stop == 0 || L.dbg_stop == 3) && sms > 0 &&
+            tiles * 2 >= static_cast<long long>(sms) * 3 && tiles < (1LL << 30)) {
+            static bool p_attr = false;
+            if (!p_attr) {   // (Engine::create sets it up front; this covers stand-alone foley_gemm calls)
+                cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+                cudaStreamIsCapturing(stream, &cs);
+                if (cs == cudaStreamCaptureStatusNone) {
+                    cudaFuncSetAttribute(gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfg::SMEM_BYTES);
+                    p_attr = true;
+                }
+            }
+            PersistTiles pt;
+            pt.m_tiles = m_tiles;
+            pt.mb_total = static_cast<int>(grid.x);
+            pt.n_tiles = static_cast<int>(grid.y);
+            pt.num_tiles = static_cast<int>(tiles);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(static_cast<unsigned>(std::min<long long>(tiles, sms)));
+            cfg.blockDim = dim3(PersistCfg::THREADS);
+            cfg.dynamicSmemBytes = PersistCfg::SMEM_BYTES;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = pdl_enabled() ? 1 : 0;
+            e = cudaLaunchKernelEx(&cfg, gemm_persistent_kernel, ma, mb, mc, args, pt);
+            if (e != cudaSuccess) {
+                if (err) *err = std::string("persistent GEMM launch failed: ") + cudaGetErrorString(e);
+                return false;
+            }
+            return true;
+        }
+    }
     if (!tf32) {
         if (L.bn == 64) e = launch_gemm_inst<64, false>(ma, mb, mc, args, grid, stream);
         else if (L.bn == 128) e = pair ? launch_gemm_inst<128, false, true>(ma, mb, mc, args, grid, stream)

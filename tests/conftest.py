@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# The GEMM launcher reads this once per process: 2 = also send fp32-partial outputs through the persistent kernel (the
+# product default, 1, keeps them on the one-tile kernel), so the GPU suite covers both kernels for every epilogue mode.
+os.environ.setdefault("FOLEY_GEMM_PERSIST", "2")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
