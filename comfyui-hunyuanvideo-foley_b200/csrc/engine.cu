@@ -394,12 +394,16 @@ foley_status Engine::alloc_plan(int B, int U, int L, int Lv, int S, int T) {
         ST_OK(palloc(&sc_kv, UT * NT * 2 * C));
         ST_OK(palloc(&sc_v1, ULv * C));
         ST_OK(palloc(&sc_idx, L));
+        ST_OK(palloc(&uq_first, US));
+        ST_OK(palloc(&uq_src, US));
+        ST_OK(palloc(&uq_tok_row, static_cast<size_t>(U) * L));
     }
     p.valid = true;
     plan = p;
     // group-dependent buffers are (re)sized by prepare_timesteps
     vectok_act = nullptr; mod_single = nullptr; vec_all = nullptr; mod_triple = nullptr; sigmas_dev = nullptr; t_dev = nullptr;
     sol_d[0] = sol_d[1] = sol_d[2] = sol_samp = nullptr; sol_table = nullptr; sol_table_cap = 0;
+    mod_rows_cap = 0;
     plan.n_t = 0;
     return FOLEY_OK;
 }
@@ -560,6 +564,27 @@ foley_status Engine::set_conditions(const void* clip, const void* sync, const vo
         gather_rows_kernel<<<blocks_for(static_cast<long long>(U) * L * C / 8, 256), 256, 0, st>>>(s3, idx_dev, U, S, L, C, a_sync);
         ++launches;
     }
+    {
+        // Distinct rows of the sync-token table: the single-block modulation vectors (13 % of the reference's step) only
+        // need to be computed once per distinct row (step()).  Exact row compare on the device, grouping on the host.
+        row_first_equal_kernel<<<static_cast<unsigned>(US), 128, 0, st>>>(s3, static_cast<int>(US), C, uq_first);
+        ++launches;
+        std::vector<int> first(US), src, id(US), idx(L), tok(static_cast<size_t>(U) * L);
+        FOLEY_CUDA_OK(cudaMemcpyAsync(first.data(), uq_first, US * sizeof(int), cudaMemcpyDeviceToHost, st));
+        FOLEY_CUDA_OK(cudaMemcpyAsync(idx.data(), idx_dev, L * sizeof(int), cudaMemcpyDeviceToHost, st));
+        FOLEY_CUDA_OK(cudaStreamSynchronize(st));
+        for (size_t r = 0; r < US; ++r) {
+            if (first[r] == static_cast<int>(r)) { id[r] = static_cast<int>(src.size()); src.push_back(static_cast<int>(r)); }
+            else id[r] = id[first[r]];
+        }
+        for (int u = 0; u < U; ++u)
+            for (int l = 0; l < L; ++l) tok[static_cast<size_t>(u) * L + l] = id[static_cast<size_t>(u) * S + idx[l]];
+        FOLEY_CUDA_OK(cudaMemcpyAsync(uq_src, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        FOLEY_CUDA_OK(cudaMemcpyAsync(uq_tok_row, tok.data(), tok.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        FOLEY_CUDA_OK(cudaStreamSynchronize(st));   // host vectors go out of scope
+        if (static_cast<int>(src.size()) != n_uq) graph_valid = false;
+        n_uq = static_cast<int>(src.size());
+    }
     // ---- RoPE tables (hifi_foley.py:797-803, 151-166, 865; positions per oracle.interleaved_positions)
     if (!tables_ready) {
         std::vector<int> pa(L), pv(Lv), pp(std::max(L, std::max(Lv, T)));
@@ -611,7 +636,8 @@ foley_status Engine::prepare_timesteps(const float* t_host, int n_t, bool per_sa
     if (!plan.valid) return fail(FOLEY_ERR_STATE, "conditions not set");
     Plan& p = plan;
     const int G = per_sample ? p.B2 : p.U;
-    if (n_t > p.n_t || G > p.G || !vec_all || !mod_single) {
+    const size_t need_rows = static_cast<size_t>(per_sample ? G : 1) * p.U * p.S;
+    if (n_t > p.n_t || G > p.G || !vec_all || !mod_single || need_rows > mod_rows_cap) {
         // (re)allocate timestep- and group-sized buffers
         p.n_t = std::max(n_t, p.n_t);
         p.G = std::max(G, p.G);
@@ -619,8 +645,11 @@ foley_status Engine::prepare_timesteps(const float* t_host, int n_t, bool per_sa
         ST_OK(palloc(&mod_triple, static_cast<size_t>(p.n_t) * NT * 18 * C));
         ST_OK(palloc(&t_dev, p.n_t));
         ST_OK(palloc(&sigmas_dev, p.n_t + 1));
-        ST_OK(palloc(&vectok_act, static_cast<size_t>(p.G) * p.S * C));
-        ST_OK(palloc(&mod_single, static_cast<size_t>(p.G) * p.S * NS * 6 * C));
+        // rows: the distinct sync-token rows (<= U*S), once per time vector (one, or one per group when timesteps are per sample)
+        const size_t mod_rows = std::max(need_rows, mod_rows_cap);
+        ST_OK(palloc(&vectok_act, mod_rows * C));
+        ST_OK(palloc(&mod_single, mod_rows * NS * 6 * C));
+        mod_rows_cap = mod_rows;
         ST_OK(palloc(&sc_e, static_cast<size_t>(p.n_t) * cfg.freq_dim));
         ST_OK(palloc(&sc_h1, static_cast<size_t>(p.n_t) * C));
         ST_OK(palloc(&sc_vs, static_cast<size_t>(p.n_t) * C));
@@ -651,6 +680,8 @@ foley_status Engine::prepare_timesteps(const float* t_host, int n_t, bool per_sa
     FOLEY_CUDA_OK(cudaMemsetAsync(step_dev, 0, 4 * sizeof(int), st));
     FOLEY_CUDA_OK(cudaStreamSynchronize(st));  // host vectors go out of scope
     cur_G = G;
+    if (cur_per_sample != per_sample) graph_valid = false;
+    cur_per_sample = per_sample;
     return FOLEY_OK;
 }
 
@@ -670,10 +701,11 @@ foley_status Engine::step(cudaStream_t st) {
     // the S sync tokens (hifi_foley.py:755-762): audio token l carries a copy of sync token idx[l].  They are computed
     // once per SYNC token (S ~ L/2 rows) and looked up through the index table — less than half of the reference's
     // modulation FLOPs (13 % of the step) for bit-identical values.
-    const int S = p.S;
+    // (set_conditions finds the n_uq distinct rows of the sync-token table and the row of every (condition, token).)
+    const int G_eff = cur_per_sample ? G : 1;   // groups only differ in their time vector when timesteps are per sample
     auto smod = [&](int blk) {
-        ModRef m; m.base = mod_single + static_cast<long long>(blk) * 6 * C; m.sample_stride = ms_tok * S;
-        m.tok_stride = ms_tok; m.by_trow = 0; m.tok_map = sc_idx; return m;
+        ModRef m; m.base = mod_single + static_cast<long long>(blk) * 6 * C; m.sample_stride = cur_per_sample ? ms_tok * n_uq : 0;
+        m.tok_stride = ms_tok; m.by_trow = 0; m.tok_map = uq_tok_row; return m;
     };
     auto bf = [&](bf16* out, long long ldo, const bf16* bias, int act, int mode = EPI_BF16) {
         GemmEpi e; e.mode = mode; e.act = act; e.out = out; e.ldo = ldo; e.bias = bias; return e;
@@ -713,12 +745,12 @@ foley_status Engine::step(cudaStream_t st) {
             FOLEY_CUDA_OK(cudaEventRecord(ev_fork, st));
             FOLEY_CUDA_OK(cudaStreamWaitEvent(sm_, ev_fork, 0));
         }
-        const long long n4 = static_cast<long long>(G) * S * C / 4;
-        FOLEY_CUDA_OK(launch_k(vectok_silu_kernel, dim3(blocks_for(n4, 256)), dim3(256), 0, sm_, sc_s3, vec_all, cond_of_grp,
-                               trow_of_grp, G, S, C, vectok_act));
+        const long long n4 = static_cast<long long>(G_eff) * n_uq * C / 4;
+        FOLEY_CUDA_OK(launch_k(vectok_silu_kernel, dim3(blocks_for(n4, 256)), dim3(256), 0, sm_, sc_s3, vec_all, uq_src,
+                               trow_of_grp, G_eff, n_uq, C, vectok_act));
         ++launches;
         skip_gemm_once = (debug_skip >> 3) & 1;
-        ST_OK(gemm(sm_, vectok_act, G * S, 1, C, 0, mod_single_all, 0, NS * 6 * C,
+        ST_OK(gemm(sm_, vectok_act, G_eff * n_uq, 1, C, 0, mod_single_all, 0, NS * 6 * C,
                    bf(mod_single, ms_tok, mod_single_all.b, 0), 1, 256));
         if (mod_branch) FOLEY_CUDA_OK(cudaEventRecord(ev_mod, sm_));
     }

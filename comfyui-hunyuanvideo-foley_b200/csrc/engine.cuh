@@ -101,6 +101,10 @@ class Engine {
     int sol_table_cap = 0;
     int64_t graph_launches_per_step = 0;
     int cur_G = 1;
+    bool cur_per_sample = false;         // timesteps differ per sample (foley_dit_forward with n_t > 1)
+    int *uq_first = nullptr, *uq_src = nullptr, *uq_tok_row = nullptr;   // distinct rows of the sync-token table (set_conditions)
+    int n_uq = 0;
+    size_t mod_rows_cap = 0;             // rows the single-block modulation buffers are allocated for
     int num_sms = 148;
     cudaStream_t side_stream = nullptr;  // visual-stream branch of the step
     cudaStream_t mod_stream = nullptr;   // single-block modulation GEMM branch

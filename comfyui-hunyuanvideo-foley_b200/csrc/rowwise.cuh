@@ -19,7 +19,8 @@ struct ModRef {
     long long sample_stride = 0;
     long long tok_stride = 0;
     int by_trow = 0;
-    const int* tok_map = nullptr;   // per-token vectors stored once per SOURCE token: row of token l is tok_map[l]
+    const int* tok_map = nullptr;   // per-token vectors stored once per DISTINCT source row: row of token l of condition
+                                    // c is tok_map[c * L + l] (rows of all conditions share one table)
 };
 
 struct RowMap {
@@ -32,7 +33,7 @@ struct RowMap {
 __device__ __forceinline__ const __nv_bfloat16* mod_ptr(const ModRef& m, const RowMap& rm, int b, int l, int chunk, int C) {
     const int g = rm.grp_of_sample[b];
     const long long s = m.by_trow ? rm.trow_of_grp[g] : g;
-    const int lt = m.tok_map ? m.tok_map[l] : l;
+    const int lt = m.tok_map ? m.tok_map[rm.cond_of_grp[g] * rm.L + l] : l;
     return m.base + s * m.sample_stride + static_cast<long long>(lt) * m.tok_stride + static_cast<long long>(chunk) * C;
 }
 
@@ -280,28 +281,54 @@ __global__ void silu_bf16_kernel(const __nv_bfloat16* in, __nv_bfloat16* out, lo
     out[i] = __float2bfloat16_rn(x / (1.0f + expf(-x)));
 }
 
-// out[g, l, :] = bf16r(silu(float(a_sync[cond(g), l, :]) + float(vec[trow(g), :])))   (hifi_foley.py:866-867
-// followed by ModulateDiT's SiLU on the fp32 per-token condition)
-__global__ void vectok_silu_kernel(const __nv_bfloat16* a_sync, const __nv_bfloat16* vec, const int* cond_of_grp,
-                                   const int* trow_of_grp, int G, int L, int C, __nv_bfloat16* out) {
+// out[ge, k, :] = bf16r(silu(float(src[row_src[k], :]) + float(vec[trow(ge), :])))   (hifi_foley.py:866-867 followed by
+// ModulateDiT's SiLU on the fp32 per-token condition), for the n_rows DISTINCT rows of the sync-token table and
+// G_eff time vectors.
+__global__ void vectok_silu_kernel(const __nv_bfloat16* src, const __nv_bfloat16* vec, const int* row_src,
+                                   const int* trow_of_grp, int G_eff, int n_rows, int C, __nv_bfloat16* out) {
     pdl_wait();
     pdl_trigger();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long n4 = static_cast<long long>(G) * L * C / 4;
+    const long long n4 = static_cast<long long>(G_eff) * n_rows * C / 4;
     if (i >= n4) return;
     const long long e = i * 4;
     const int c = static_cast<int>(e % C);
-    const long long gl = e / C;
-    const int l = static_cast<int>(gl % L), g = static_cast<int>(gl / L);
+    const long long gk = e / C;
+    const int k = static_cast<int>(gk % n_rows), ge = static_cast<int>(gk / n_rows);
     float a[4], v[4], o[4];
-    load_bf16x4(a_sync + (static_cast<long long>(cond_of_grp[g]) * L + l) * C + c, a);
-    load_bf16x4(vec + static_cast<long long>(trow_of_grp[g]) * C + c, v);
+    load_bf16x4(src + static_cast<long long>(row_src[k]) * C + c, a);
+    load_bf16x4(vec + static_cast<long long>(trow_of_grp[ge]) * C + c, v);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float s = a[j] + v[j];
         o[j] = s / (1.0f + expf(-s));
     }
     store_bf16x4(out + e, o);
+}
+
+// first[r] = smallest r' <= r whose row equals row r (exact, 16-byte compares): finds the distinct rows of the sync-token
+// table (the unconditional half repeats with period 8, text-to-audio repeats everywhere).  One CTA per row.
+__global__ void row_first_equal_kernel(const __nv_bfloat16* rows, int n_rows, int C, int* first) {
+    const int r = blockIdx.x;
+    __shared__ int differs;
+    const uint4* mine = reinterpret_cast<const uint4*>(rows + static_cast<long long>(r) * C);
+    const int n16 = C / 8;
+    int found = r;
+    for (int cand = 0; cand < r; ++cand) {
+        if (threadIdx.x == 0) differs = 0;
+        __syncthreads();
+        const uint4* other = reinterpret_cast<const uint4*>(rows + static_cast<long long>(cand) * C);
+        int d = 0;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) {
+            const uint4 a = mine[i], b = other[i];
+            d |= (a.x != b.x) | (a.y != b.y) | (a.z != b.z) | (a.w != b.w);
+        }
+        if (d) differs = 1;
+        __syncthreads();
+        if (!differs) { found = cand; break; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) first[r] = found;
 }
 
 // sync features: out[u, s, :] = bf16r(sync[u, s, :] + pos_emb[s % 8, :])   (hifi_foley.py:757-758)
