@@ -202,6 +202,23 @@ extern "C" foley_status foley_denoise_solver(foley_engine* e, float* latents, co
     API_GUARD_END
 }
 
+// Host only: the stage table foley_denoise_solver uploads (one row of 9 numbers per model call):
+// dt, c0, c1, c2, cm, kind, store_slot, save_sample, base_saved.
+extern "C" foley_status foley_solver_table(int32_t solver, const float* sigmas, int32_t n_calls, float* out9) {
+    if (!sigmas || !out9 || n_calls < 1) return fail(FOLEY_ERR_INVALID, "foley_solver_table: bad argument");
+    if (solver < FOLEY_SOLVER_HEUN2 || solver > FOLEY_SOLVER_KUTTA4) return fail(FOLEY_ERR_INVALID, "foley_solver_table: multi-stage solvers only");
+    API_GUARD_BEGIN
+    const std::vector<SolverCall> t = solver_table(solver, sigmas, n_calls);
+    for (int i = 0; i < n_calls; ++i) {
+        float* o = out9 + 9 * i;
+        o[0] = t[i].dt; o[1] = t[i].c0; o[2] = t[i].c1; o[3] = t[i].c2; o[4] = t[i].cm;
+        o[5] = static_cast<float>(t[i].kind); o[6] = static_cast<float>(t[i].store_slot);
+        o[7] = static_cast<float>(t[i].save_sample); o[8] = static_cast<float>(t[i].base_saved);
+    }
+    return FOLEY_OK;
+    API_GUARD_END
+}
+
 extern "C" foley_status foley_dac_decode(foley_engine* e, const float* z, int32_t batch, int32_t L, float* wav,
                                          void* stream) {
     if (!e || !z || !wav) return fail(FOLEY_ERR_INVALID, "foley_dac_decode: null argument");

@@ -957,7 +957,7 @@ foley_status Engine::forward(const float* x, const float* t, int n_t, float* out
 // Per-call stage table of the reference scheduler's multi-stage solvers (scheduling_flow_match_discrete.py:299-373).
 // Call i feeds timesteps[i] to the model (utils.py:215-246) while sigma / sigma_next come from `step_index`, which
 // only advances after a solver's last stage.
-static std::vector<SolverCall> solver_table(int solver, const float* sigmas, int n_calls) {
+std::vector<SolverCall> solver_table(int solver, const float* sigmas, int n_calls) {
     const int n_stages = solver == FOLEY_SOLVER_KUTTA4 ? 4 : 2;
     std::vector<SolverCall> tab(n_calls);
     int step_index = 0, stage = 0;

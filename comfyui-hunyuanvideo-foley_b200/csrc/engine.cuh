@@ -50,6 +50,9 @@ struct Plan {                     // shapes of the current generation
     bool valid = false;
 };
 
+// Per-call stage table of the multi-stage solvers (engine.cu); exported through foley_solver_table for host-side tests.
+std::vector<SolverCall> solver_table(int solver, const float* sigmas, int n_calls);
+
 class Engine {
   public:
     foley_config cfg{};

@@ -16,6 +16,9 @@
 #pragma once
 #include "ptx.cuh"
 
+#ifndef FOLEY_SWIGLU_STAGED
+#define FOLEY_SWIGLU_STAGED 0     // 1: SwiGLU tiles also leave through the staging buffer (measured 0.8 us slower per tile)
+#endif
 #ifndef FOLEY_EPI_WARPS_BF16
 #define FOLEY_EPI_WARPS_BF16 8    // 16 measured: fc1 (GELU) 14.5 -> 13.7 us, but w2 / w1|w3 0.3 us slower; step 4.14 -> 4.17 ms
 #endif
@@ -296,9 +299,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         const bool row_ok = r < g.rows;
         const long long row_off = static_cast<long long>(batch) * e.out_batch_stride +
                                   static_cast<long long>(r) * e.ldo;
-#ifndef FOLEY_SWIGLU_STAGED
-#define FOLEY_SWIGLU_STAGED 0
-#endif
         // SwiGLU tiles write only 32 bytes per row and chunk: their direct stores were never the bottleneck, and the
         // staged path costs them ~0.7 us of barriers (measured), so they keep storing from registers.
         if (e.mode != EPI_DAC && (FOLEY_SWIGLU_STAGED ? !(BN == 64 && e.mode == EPI_SWIGLU) : e.mode != EPI_SWIGLU)) {

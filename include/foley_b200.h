@@ -132,6 +132,11 @@ foley_status foley_denoise_solver(foley_engine* e, float* latents, const float* 
                                   float guidance, int32_t solver, foley_progress_fn progress, void* user,
                                   void* stream);
 
+/* Host only (tests): the per-call stage table foley_denoise_solver runs from — 9 floats per model call: dt, the four
+ * derivative coefficients c0 c1 c2 cm, kind (0 model output / 1 Heun / 2 Kutta combination), derivative slot to keep
+ * (-1 none), save-base-sample flag, update-from-saved-base flag. */
+foley_status foley_solver_table(int32_t solver, const float* sigmas, int32_t n_calls, float* out9);
+
 /* ---- DAC-VAE decode (dac.py:280-303) ----------------------------------------------------------
  * z: [batch, latent_dim, L] f32 -> wav: [batch, 1, L*hop] f32 (hop = 960). */
 foley_status foley_dac_decode(foley_engine* e, const float* z, int32_t batch, int32_t L, float* wav,

@@ -341,3 +341,44 @@ def test_safetensors_probe_and_header_parser(tmp_path):
         assert lib.foley_safetensors_probe(p.encode(), None, None, None) == 1, name
         assert b"safetensors" in lib.foley_last_error()
     assert lib.foley_safetensors_probe(str(tmp_path / "missing.safetensors").encode(), None, None, None) == 1
+
+
+def test_engine_solver_stage_table_replays_the_reference_scheduler():
+    """foley_solver_table (the host half of foley_denoise_solver) applied with numpy in separately rounded fp32 must give
+    the same numbers, bit for bit, as the reference scheduler's stage machine (sampling.FlowMatchSolverState) on a
+    random derivative sequence — for call counts that end mid-stage too."""
+    import numpy as np
+    sampling, E = load_pkg("sampling"), load_pkg("engine")
+    lib = E.load_library()
+    lib.foley_solver_table.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_float), ctypes.c_int32, ctypes.POINTER(ctypes.c_float)]
+    g = torch.Generator().manual_seed(0)
+    for solver, sid in (("heun-2", 1), ("midpoint-2", 2), ("kutta-4", 3)):
+        for n in (1, 4, 7, 10):
+            sig = sampling.sigma_schedule(n, 1.0 if n % 2 else 3.0).float()
+            arr = (ctypes.c_float * (n + 1))(*sig.tolist())
+            out = (ctypes.c_float * (9 * n))()
+            assert lib.foley_solver_table(sid, arr, n, out) == 0
+            tab = np.array(out, dtype=np.float32).reshape(n, 9)
+            st = sampling.FlowMatchSolverState(solver, sig)
+            x_ref = torch.randn(2, 4, 5, generator=g)
+            x = x_ref.numpy().copy()
+            d = [None, None, None]
+            base = None
+            for i in range(n):
+                mo = torch.randn(2, 4, 5, generator=g)
+                x_ref = st.step(mo, x_ref)
+                dt, c0, c1, c2, cm, kind, slot, save, use_base = tab[i]
+                m = mo.numpy()
+                if save:
+                    base = x.copy()
+                if slot >= 0:
+                    d[int(slot)] = m.copy()
+                if kind == 1:
+                    der = np.float32(0.5) * (d[0] + m)
+                elif kind == 2:
+                    der = ((c0 * d[0] + c1 * d[1]) + c2 * d[2]) + cm * m
+                else:
+                    der = m
+                x = ((base if use_base else x) + der * dt).astype(np.float32)
+                assert np.array_equal(x, x_ref.numpy()), (solver, n, i)
+    assert lib.foley_solver_table(0, arr, n, out) == 1     # Euler has no stage table
