@@ -57,7 +57,8 @@ struct GemmArgs {
     int tap_off0;    // A row offset of tap 0
     int tap_stride;  // A row offset increment per tap
     int splits;      // K splits (gridDim.z); the taps*kb_per_tap k-blocks are divided evenly
-    int dbg_stop;    // bring-up aid: 1 = setup only, 2 = TMA only, 3 = TMA+MMA, 0 = full kernel
+    int dbg_stop;    // bring-up aid: 0 = full kernel, 1 = setup only, 2 = TMA only, 3 = TMA+MMA, 4 = MMA only (first ring
+                     // pass re-used), 8 = full kernel + clock64 stamps of CTA 0 (foley_debug_times)
     int prefetch_b;  // L2 prefetch distance of the weight operand in k-blocks (0 = off)
     int pf_mod;      // CTAs with blockIdx.x % pf_mod == 0 issue the prefetch (m-tiles sharing a weight column)
     GemmEpi epi;

@@ -20,7 +20,8 @@ ap.add_argument("--splits", type=int, default=0)
 ap.add_argument("--iters", type=int, default=50)
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--all", action="store_true")
-ap.add_argument("--dbg", type=int, default=0, help="partial pipeline: 2 = TMA only, 3 = TMA+MMA (no epilogue)")
+ap.add_argument("--dbg", type=int, default=0, help="bring-up modes: 1 = setup only, 2 = TMA only, 3 = TMA+MMA (no epilogue), 4 = MMA only on a re-used "
+                                                       "ring, 8 = full kernel + clock64 timeline of CTA 0")
 a = ap.parse_args()
 lib = ctypes.CDLL(os.environ.get("FOLEY_B200_LIB", os.path.join(ROOT, "comfyui-hunyuanvideo-foley_b200", "libfoley_b200.so")))
 lib.foley_last_error.restype = ctypes.c_char_p
