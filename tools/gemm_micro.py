@@ -26,7 +26,8 @@ a = ap.parse_args()
 lib = ctypes.CDLL(os.environ.get("FOLEY_B200_LIB", os.path.join(ROOT, "comfyui-hunyuanvideo-foley_b200", "libfoley_b200.so")))
 lib.foley_last_error.restype = ctypes.c_char_p
 i64, i32, vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p
-lib.foley_debug_times.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
+if hasattr(lib, "foley_debug_times"):   # (absent from older builds loaded through FOLEY_B200_LIB for A/B runs)
+    lib.foley_debug_times.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
 lib.foley_gemm.argtypes = [vp, i32, i64, i64, i64, i64, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, i64, i64,
                            i64, vp]
 c = SY.model_config(a.model)
