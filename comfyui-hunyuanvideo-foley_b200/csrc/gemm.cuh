@@ -16,6 +16,9 @@
 #pragma once
 #include "ptx.cuh"
 
+#ifndef FOLEY_GEMM_TWO_PRODUCERS
+#define FOLEY_GEMM_TWO_PRODUCERS 1   // 0: warp 0 issues both loads of a k-block (A/B switch for the round-2 bisect of the w1|w3 shape)
+#endif
 #ifndef FOLEY_SWIGLU_STAGED
 #define FOLEY_SWIGLU_STAGED 0     // 1: SwiGLU tiles also leave through the staging buffer (measured 0.8 us slower per tile)
 #endif
@@ -175,6 +178,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // setup / teardown only
     } else if (warp == 0) {
         // ------------------------------------------------------------- TMA producer: weight tiles past the first ring pass
+#if FOLEY_GEMM_TWO_PRODUCERS
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 1;   // round r >= 1 waits for the consumer's release of round r-1: parity (r & 1) ^ 1
@@ -184,9 +188,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
             }
         }
+#else
+        if (lane == 0) {   // one thread issues both operands (same barrier protocol: two expect_tx arrivals per stage)
+            int tap = kb_begin / g.kb_per_tap;
+            int kk = kb_begin - tap * g.kb_per_tap;
+            int arow = m0 + g.tap_off0 + tap * g.tap_stride;
+            int s = 0;
+            uint32_t ph = 0;
+            pdl_wait();
+            for (int i = 0; i < (g.dbg_stop == 4 ? pre : num_kb); ++i) {
+                if (i >= pre) {
+                    if (!mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + i)) break;
+                    load_b(s, kb_begin + i);
+                }
+                mbar_expect_tx(&full_bar[s], Cfg::A_BYTES);
+                tma_load_3d(smem_a + s * Cfg::A_BYTES, &tm_a, &full_bar[s], kk * Cfg::BK, arow, batch);
+                if (++kk == g.kb_per_tap) { kk = 0; arow += g.tap_stride; }
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+#endif
     } else if (warp == Cfg::A_WARP) {
         // ------------------------------------------------------------- TMA producer: activation tiles
-        if (lane == 0) {
+        if (lane == 0 && FOLEY_GEMM_TWO_PRODUCERS) {
             int tap = kb_begin / g.kb_per_tap;
             int kk = kb_begin - tap * g.kb_per_tap;
             int arow = m0 + g.tap_off0 + tap * g.tap_stride;
