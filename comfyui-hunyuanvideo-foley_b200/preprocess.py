@@ -3,7 +3,6 @@ nodes.py:293-317 (frame count, hold-last-frame padding, 8 / 25 fps picks) over `
 `(image*255).byte()` + torchvision's uint8 antialiased-bicubic Resize [+ CenterCrop] + ToDtype(scale) + Normalize(0.5, 0.5)
 (nodes.py:184-196) into two HBM-bound kernels, bit-exact with the reference's per-frame CPU path.  No CPU fallback.
 """
-import ctypes
 from ctypes import c_int32, c_void_p
 
 import torch
