@@ -88,8 +88,8 @@ struct GemmCfg {
     // kernels always keep 8: their epilogue needs > 100 registers.
     static constexpr int EPI_WARPS = FOLEY_EPI_WARPS_BF16 == 16 && !kTF32 ? 16 : 8;
     static constexpr int EPI_GROUPS = EPI_WARPS / 4;          // warps per TMEM lane quarter = interleaved column-chunk sets
-    static constexpr int A_WARP = 2 + EPI_WARPS;              // warp id of the activation producer
-    static constexpr int THREADS = 32 * (3 + EPI_WARPS);
+    static constexpr int A_WARP = FOLEY_GEMM_TWO_PRODUCERS ? 2 + EPI_WARPS : -1;   // warp id of the activation producer
+    static constexpr int THREADS = 32 * (2 + EPI_WARPS + (FOLEY_GEMM_TWO_PRODUCERS ? 1 : 0));
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
