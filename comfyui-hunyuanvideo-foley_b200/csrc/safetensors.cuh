@@ -220,7 +220,12 @@ class StFile {
             const int eb = st_dtype_bytes(e.dtype);
             if (eb == 0) return bad("unknown dtype " + e.dtype + " for " + e.name, err);
             uint64_t numel = 1;
-            for (int64_t d : e.shape) numel *= static_cast<uint64_t>(d);
+            bool overflow = false;
+            for (int64_t d : e.shape) {
+                if (d < 0 || (d != 0 && numel > (1ull << 46) / static_cast<uint64_t>(d))) { overflow = true; break; }
+                numel *= static_cast<uint64_t>(d);
+            }
+            if (overflow) return bad("shape of " + e.name + " is out of range", err);
             if (e.end > data_bytes || e.end - e.begin != numel * static_cast<uint64_t>(eb))
                 return bad("data_offsets do not match shape/dtype for " + e.name, err);
         }

@@ -382,3 +382,61 @@ def test_engine_solver_stage_table_replays_the_reference_scheduler():
                 x = ((base if use_base else x) + der * dt).astype(np.float32)
                 assert np.array_equal(x, x_ref.numpy()), (solver, n, i)
     assert lib.foley_solver_table(0, arr, n, out) == 1     # Euler has no stage table
+
+
+def test_safetensors_parser_survives_mutated_files(tmp_path):
+    """Native header parser hardening: a few thousand mutated / truncated / re-headered files must be either accepted or
+    refused with an error — never crash, never report sizes beyond the file."""
+    import random
+    import struct
+    E, ck = load_pkg("engine"), load_pkg("checkpoint")
+    lib = E.load_library()
+    g = torch.Generator().manual_seed(0)
+    base = str(tmp_path / "b.safetensors")
+    ck.write_safetensors(base, {"a.weight": torch.randn(8, 4, generator=g).bfloat16(), "b": torch.randn(3, generator=g),
+                                "c.weight": torch.randn(2, 4, 3, generator=g).half()}, metadata={"format": "pt"})
+    raw = bytearray(open(base, "rb").read())
+    (hlen,) = struct.unpack("<Q", raw[:8])
+    rng = random.Random(1)
+    p = str(tmp_path / "m.safetensors")
+    seen = {0: 0, 1: 0}
+    for _ in range(1500):
+        b = bytearray(raw)
+        mode = rng.randrange(6)
+        if mode == 0:
+            for _k in range(rng.randrange(1, 6)):
+                b[8 + rng.randrange(hlen)] = rng.randrange(256)
+        elif mode == 1:
+            b = b[:rng.randrange(0, len(b))]
+        elif mode == 2:
+            b[:8] = struct.pack("<Q", rng.choice([0, 1, 7, hlen - 1, hlen + 1, len(b), 2 ** 40, 2 ** 63, rng.randrange(0, 2 * len(b))]))
+        elif mode == 3:
+            i = 8 + rng.randrange(hlen)
+            del b[i:min(len(b), i + rng.randrange(1, 20))]
+        elif mode == 4:
+            i = 8 + rng.randrange(hlen)
+            b[i:i] = bytes(rng.randrange(256) for _k in range(rng.randrange(1, 10)))
+        else:
+            hdr = json.loads(bytes(raw[8:8 + hlen]))
+            k = rng.choice([k for k in hdr if k != "__metadata__"])
+            ch = rng.randrange(5)
+            if ch == 0:
+                hdr[k]["data_offsets"] = [rng.randrange(0, 2 ** 62), rng.randrange(0, 2 ** 62)]
+            elif ch == 1:
+                hdr[k]["shape"] = [rng.randrange(0, 2 ** 40) for _k in range(rng.randrange(0, 6))]
+            elif ch == 2:
+                hdr[k]["dtype"] = rng.choice(["F8_E4M3", "I64", "X", "", "F32"])
+            elif ch == 3:
+                hdr["__metadata__"] = {"a": {"b": [1, 2, {"c": None}]}, "x": "y\\\"z"}
+            else:
+                hdr[k] = rng.choice([[], 3, "s", {"dtype": "F32"}])
+            hj = json.dumps(hdr).encode()
+            b = bytearray(struct.pack("<Q", len(hj)) + hj + bytes(raw[8 + hlen:]))
+        open(p, "wb").write(b)
+        n, nb = ctypes.c_int64(), ctypes.c_int64()
+        st = lib.foley_safetensors_probe(p.encode(), ctypes.byref(n), ctypes.byref(nb), None)
+        assert st in (0, 1)
+        if st == 0:
+            assert 0 <= nb.value <= len(b)
+        seen[st] += 1
+    assert seen[0] > 0 and seen[1] > 0
