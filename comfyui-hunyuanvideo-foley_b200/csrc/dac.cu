@@ -161,8 +161,14 @@ static foley_status folded_weight(Engine* e, const std::string& base, bool weigh
     return FOLEY_OK;
 }
 
+void delete_dac_layer(DacLayer* l) { delete l; }
+
 foley_status Engine::dac_finalize() {
     if (dac_ready) return FOLEY_OK;
+    if (!dac_layers.empty() || !dac_allocs.empty()) {   // DAC weights reloaded: drop the previous packed decoder
+        FOLEY_CUDA_OK(cudaDeviceSynchronize());
+        free_dac();
+    }
     const std::string P = "dac.";
     auto keep = [&](void* p) { dac_allocs.push_back(p); };
     auto vec = [&](const std::string& name, float** out) -> foley_status {

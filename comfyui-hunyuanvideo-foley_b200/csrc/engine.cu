@@ -21,6 +21,38 @@ namespace foley {
 static inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
 // ------------------------------------------------------------------------------------------------ lifetime
+// Releases the packed (GEMM-layout) DiT weights: before a re-finalize and at destruction.
+void Engine::free_packed() {
+    auto fl = [](LinearW& w) { if (w.w) cudaFree(w.w); if (w.b) cudaFree(w.b); w = LinearW(); };
+    for (LinearW* w : {&audio_embed, &vis_w13, &vis_w2, &cond1, &cond2, &time1, &time2, &sync0, &sync_w13, &sync_w2,
+                       &final_lin, &mod_triple_all, &mod_single_all, &text_kv_all})
+        fl(*w);
+    auto fv = [](bf16*& p) { if (p) cudaFree(p); p = nullptr; };
+    for (auto& t : triple) {
+        for (int s = 0; s < 2; ++s) {
+            fl(t.qkv[s]); fl(t.self_proj[s]); fl(t.cross_q[s]); fl(t.cross_proj[s]); fl(t.fc1[s]); fl(t.fc2[s]);
+            fv(t.self_q_norm[s]); fv(t.self_k_norm[s]); fv(t.cross_q_norm[s]);
+        }
+        fv(t.text_k_norm);
+    }
+    for (auto& s : single) {
+        fl(s.qkv); fl(s.linear1); fl(s.w13); fl(s.w2);
+        fv(s.q_norm); fv(s.k_norm);
+    }
+    fv(sync_pos_emb); fv(empty_clip); fv(empty_sync);
+    packed = false;
+}
+
+void Engine::free_dac() {
+    for (DacLayer* l : dac_layers) delete_dac_layer(l);
+    dac_layers.clear();
+    for (void* p : dac_allocs) cudaFree(p);
+    dac_allocs.clear();
+    for (int i = 0; i < 4; ++i) dac_buf[i] = nullptr;
+    dac_buf_elems = 0;
+    dac_ready = false;
+}
+
 Engine::~Engine() {
     cudaSetDevice(device);
     if (step_graph) cudaGraphExecDestroy(step_graph);
@@ -33,24 +65,8 @@ Engine::~Engine() {
     free_plan();
     for (auto& kv : raw)
         if (kv.second.dev) cudaFree(kv.second.dev);
-    auto fl = [](LinearW& w) { if (w.w) cudaFree(w.w); if (w.b) cudaFree(w.b); w.w = w.b = nullptr; };
-    for (LinearW* w : {&audio_embed, &vis_w13, &vis_w2, &cond1, &cond2, &time1, &time2, &sync0, &sync_w13, &sync_w2,
-                       &final_lin, &mod_triple_all, &mod_single_all, &text_kv_all})
-        fl(*w);
-    for (auto& t : triple) {
-        for (int s = 0; s < 2; ++s) {
-            fl(t.qkv[s]); fl(t.self_proj[s]); fl(t.cross_q[s]); fl(t.cross_proj[s]); fl(t.fc1[s]); fl(t.fc2[s]);
-            for (bf16* p : {t.self_q_norm[s], t.self_k_norm[s], t.cross_q_norm[s]}) if (p) cudaFree(p);
-        }
-        if (t.text_k_norm) cudaFree(t.text_k_norm);
-    }
-    for (auto& s : single) {
-        fl(s.qkv); fl(s.linear1); fl(s.w13); fl(s.w2);
-        if (s.q_norm) cudaFree(s.q_norm);
-        if (s.k_norm) cudaFree(s.k_norm);
-    }
-    for (bf16* p : {sync_pos_emb, empty_clip, empty_sync}) if (p) cudaFree(p);
-    for (void* p : dac_allocs) cudaFree(p);
+    free_packed();
+    free_dac();
 }
 
 foley_status Engine::create(const foley_config* c, int dev) {
@@ -117,7 +133,11 @@ foley_status Engine::load_tensor(const char* name, const void* data, const int64
     auto it = raw.find(n);
     if (it != raw.end() && it->second.dev) cudaFree(it->second.dev);
     raw[n] = rt;
-    finalized = false;
+    // A (re)loaded tensor invalidates only the half of the engine it belongs to: DAC tensors are packed by
+    // dac_finalize, everything else by finalize (which frees the staging copies, so a reload must bring the whole
+    // state dict again; finalize says which tensor is missing otherwise).
+    if (n.rfind("dac.", 0) == 0) dac_ready = false;
+    else finalized = false;
     return FOLEY_OK;
 }
 
@@ -226,8 +246,18 @@ static foley_status take_pair(Engine* e, const std::string& n1, const std::strin
 }
 
 foley_status Engine::finalize() {
-    if (finalized) return FOLEY_OK;
+    if (finalized) {
+        if (cfg.with_dac && !dac_ready) ST_OK(dac_finalize());
+        return FOLEY_OK;
+    }
     FOLEY_CUDA_OK(cudaSetDevice(device));
+    if (packed) {   // weights were reloaded after an earlier finalize: drop the old packed copies (and what was built on them)
+        FOLEY_CUDA_OK(cudaDeviceSynchronize());
+        free_plan();
+        if (step_graph) { cudaGraphExecDestroy(step_graph); step_graph = nullptr; }
+        free_packed();
+    }
+    packed = true;
     ST_OK(take_linear("audio_embedder.proj", &audio_embed, true, 1));
     ST_OK(take_pair(this, "visual_proj.w1", "visual_proj.w3", &vis_w13, 1));
     ST_OK(take_linear("visual_proj.w2", &vis_w2, false, 1));
@@ -333,6 +363,16 @@ foley_status Engine::palloc(T** p, size_t count) {
     plan_allocs.push_back(d);
     *p = static_cast<T*>(d);
     return FOLEY_OK;
+}
+
+// Frees one plan-owned buffer (before it is re-allocated larger).
+template <typename T>
+void Engine::pfree(T*& p) {
+    if (!p) return;
+    auto it = std::find(plan_allocs.begin(), plan_allocs.end(), static_cast<void*>(p));
+    if (it != plan_allocs.end()) plan_allocs.erase(it);
+    cudaFree(p);
+    p = nullptr;
 }
 
 void Engine::free_plan() {
@@ -641,6 +681,9 @@ foley_status Engine::prepare_timesteps(const float* t_host, int n_t, bool per_sa
         // (re)allocate timestep- and group-sized buffers
         p.n_t = std::max(n_t, p.n_t);
         p.G = std::max(G, p.G);
+        FOLEY_CUDA_OK(cudaStreamSynchronize(st));   // the old buffers may still be read by work queued on this stream
+        pfree(vec_all); pfree(mod_triple); pfree(t_dev); pfree(sigmas_dev); pfree(vectok_act); pfree(mod_single);
+        pfree(sc_e); pfree(sc_h1); pfree(sc_vs);
         ST_OK(palloc(&vec_all, static_cast<size_t>(p.n_t) * C));
         ST_OK(palloc(&mod_triple, static_cast<size_t>(p.n_t) * NT * 18 * C));
         ST_OK(palloc(&t_dev, p.n_t));
@@ -1004,6 +1047,8 @@ foley_status Engine::denoise(float* latents, const float* sigmas, int n_steps, f
             graph_valid = false;
         }
         if (n_steps > sol_table_cap) {
+            FOLEY_CUDA_OK(cudaStreamSynchronize(st));
+            pfree(sol_table);
             ST_OK(palloc(&sol_table, static_cast<size_t>(n_steps)));
             sol_table_cap = n_steps;
             graph_valid = false;

@@ -43,7 +43,8 @@ struct SingleW {
     bf16* k_norm = nullptr;
 };
 
-struct DacLayer;  // dac.cuh
+struct DacLayer;  // dac.cu
+void delete_dac_layer(DacLayer* l);
 
 struct Plan {                     // shapes of the current generation
     int B = 0, U = 0, B2 = 0, G = 0, L = 0, Lv = 0, S = 0, T = 0, n_t = 0;
@@ -60,6 +61,7 @@ class Engine {
     int C = 0, H = 0, NT = 0, NS = 0, F = 0, Hs = 0, Hy = 0, LAT = 0;
     int64_t launches = 0;
     bool finalized = false;
+    bool packed = false;          // packed DiT weights exist (possibly stale / partial when !finalized)
     int debug_skip = 0;           // option "debug_skip": ablation bitmask for tools/ablate_step.py (results are garbage)
     bool skip_gemm_once = false;
     int fp8_storage = 0;          // option "fp8_weight_storage": the reference's quantization != none for tensors loaded next
@@ -159,7 +161,10 @@ class Engine {
                       const LinearW& W, int n_off, int n_cnt, GemmEpi epi, int splits, int bn);
     foley_status alloc_plan(int B, int U, int L, int Lv, int S, int T);
     void free_plan();
+    void free_packed();
+    void free_dac();
     template <typename T> foley_status palloc(T** p, size_t count);
+    template <typename T> void pfree(T*& p);
     int pick_splits(int rows, int batch, int n, int kblocks, int bn) const;
     int pick_bn(int rows, int batch, int n, int kblocks) const;
     void plan_gemm(int rows, int batch, int n, int kblocks, bool can_split, int* bn_out, int* splits_out, int split_cap = 0) const;

@@ -119,11 +119,13 @@ class StHeaderParser {
             return eat(']');
         }
     }
-    bool skip_value() {   // strings, numbers, literals, nested arrays / objects
+    static constexpr int kMaxDepth = 64;   // nesting limit of skipped values: recursion depth must not follow the input
+    bool skip_value(int depth = 0) {   // strings, numbers, literals, nested arrays / objects
         ws();
         const char c = peek();
         if (c == '"') { std::string s; return str(&s); }
         if (c == '{' || c == '[') {
+            if (depth >= kMaxDepth) return false;
             const char close = c == '{' ? '}' : ']';
             ++p_;
             ws();
@@ -136,7 +138,7 @@ class StHeaderParser {
                     ws();
                     if (!eat(':')) return false;
                 }
-                if (!skip_value()) return false;
+                if (!skip_value(depth + 1)) return false;
                 ws();
                 if (eat(',')) continue;
                 return eat(close);

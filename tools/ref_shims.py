@@ -1,8 +1,9 @@
 """Import shims that let the reference's hot path (/root/reference) be imported in THIS container,
 where ComfyUI, diffusers, av, accelerate are not installed.
 
-Only used by tools/make_golden.py (fixture generation) and tests that are skipped when
-/root/reference is absent.  Nothing under the product package imports this file.
+Only used by tools/make_golden.py / tools/gpu_reference_golden.py (fixture generation), bench.py --impl reference
+and tests that are skipped when no reference tree is present.  Nothing under the product package imports this file.
+The tree is looked up at $FOLEY_REFERENCE_ROOT, then baseline/_ref (tools/stage_reference.py), then /root/reference.
 """
 import importlib
 import importlib.machinery
@@ -13,7 +14,19 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("FOLEY_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")   # tools/stage_reference.py (travels to the GPU box)
+
+
+def _default_root():
+    if os.environ.get("FOLEY_REFERENCE_ROOT"):
+        return os.environ["FOLEY_REFERENCE_ROOT"]
+    if os.path.isdir(os.path.join(_STAGED, "hunyuanvideo_foley")):
+        return _STAGED
+    return "/root/reference"
+
+
+REF_ROOT = _default_root()
 
 
 def _mod(name):
