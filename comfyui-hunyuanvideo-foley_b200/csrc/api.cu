@@ -17,7 +17,10 @@ std::string& last_error_ref() {
 using namespace foley;
 
 extern "C" const char* foley_last_error(void) { return last_error_ref().c_str(); }
-extern "C" const char* foley_version(void) { return "foley_b200 0.1 sm_100a (tcgen05+TMA)"; }
+#ifndef FOLEY_SRC_HASH
+#define FOLEY_SRC_HASH "unknown"
+#endif
+extern "C" const char* foley_version(void) { return "foley_b200 0.2 sm_100a (tcgen05+TMA) src:" FOLEY_SRC_HASH; }
 
 extern "C" foley_status foley_gemm(const void* a, int32_t dtype, int64_t batch, int64_t rows, int64_t k,
                                    int64_t lda, int64_t a_batch_stride, const void* w, int64_t n,
@@ -36,6 +39,7 @@ extern "C" foley_status foley_gemm(const void* a, int32_t dtype, int64_t batch, 
     L.taps = taps; L.tap_off0 = tap_off0; L.tap_stride = tap_stride;
     L.splits = splits; L.bn = bn & 0xFFFF;
     L.dbg_stop = (bn >> 16) & 0xF;  // bring-up aid: upper bits of bn select a partial pipeline
+    L.pair = ((bn >> 20) & 3) - 1;  // 0: default policy, 1: single-CTA tiles, 2: CTA-pair (cta_group::2) tiles
     L.epi.mode = mode; L.epi.act = act; L.epi.bias = bias; L.epi.out = out; L.epi.ldo = ldo;
     L.epi.out_batch_stride = out_batch_stride; L.epi.split_stride = split_stride;
     std::string err;

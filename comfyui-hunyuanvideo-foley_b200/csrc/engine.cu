@@ -2,8 +2,10 @@
 #include "engine.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 #include "attention.cuh"
 #include "safetensors.cuh"
@@ -63,6 +65,7 @@ Engine::~Engine() {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     free_plan();
+    if (host_step) cudaFreeHost(host_step);
     for (auto& kv : raw)
         if (kv.second.dev) cudaFree(kv.second.dev);
     free_packed();
@@ -93,6 +96,9 @@ foley_status Engine::create(const foley_config* c, int dev) {
     if (const char* e = getenv("FOLEY_PLAN")) sscanf(e, "%lf,%lf,%lf,%lf", &plan_tkb128, &plan_tkb256, &plan_tfix, &plan_tsplit);
     FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    FOLEY_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&host_step), sizeof(int), cudaHostAllocMapped));
+    *host_step = 0;
+    FOLEY_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&host_step_dev), host_step, 0));
     {
         std::string err;
         if (!gemm_init_attributes(&err)) return fail(FOLEY_ERR_CUDA, err);
@@ -370,8 +376,10 @@ template <typename T>
 void Engine::pfree(T*& p) {
     if (!p) return;
     auto it = std::find(plan_allocs.begin(), plan_allocs.end(), static_cast<void*>(p));
-    if (it != plan_allocs.end()) plan_allocs.erase(it);
-    cudaFree(p);
+    if (it != plan_allocs.end()) {   // (a pointer that outlived its plan is stale: free_plan released it already)
+        plan_allocs.erase(it);
+        cudaFree(p);
+    }
     p = nullptr;
 }
 
@@ -442,6 +450,7 @@ foley_status Engine::alloc_plan(int B, int U, int L, int Lv, int S, int T) {
     plan = p;
     // group-dependent buffers are (re)sized by prepare_timesteps
     vectok_act = nullptr; mod_single = nullptr; vec_all = nullptr; mod_triple = nullptr; sigmas_dev = nullptr; t_dev = nullptr;
+    sc_e = sc_h1 = sc_vs = nullptr;
     sol_d[0] = sol_d[1] = sol_d[2] = sol_samp = nullptr; sol_table = nullptr; sol_table_cap = 0;
     mod_rows_cap = 0;
     plan.n_t = 0;
@@ -1076,7 +1085,8 @@ foley_status Engine::denoise(float* latents, const float* sigmas, int n_steps, f
         else   // the table entry decides the stage; the kernel itself is the same for every call and solver
             FOLEY_CUDA_OK(launch_k(cfg_solver_kernel, grid, blk, 0, st, y_out, lat_dev, x_in, sol_d[0], sol_d[1], sol_d[2],
                                    sol_samp, p.B, p.U, LAT, p.L, guidance, sol_table, step_dev));
-        FOLEY_CUDA_OK(launch_k(advance_step_kernel, dim3(1), dim3(32), 0, st, step_dev, trow_of_grp, cur_G));
+        FOLEY_CUDA_OK(launch_k(advance_step_kernel, dim3(1), dim3(32), 0, st, step_dev, trow_of_grp, cur_G,
+                               static_cast<volatile int*>(host_step_dev)));
         launches += 2;
         FOLEY_CUDA_OK(cudaGetLastError());
         return FOLEY_OK;
@@ -1103,19 +1113,29 @@ foley_status Engine::denoise(float* latents, const float* sigmas, int n_steps, f
         graph_solver_kind = solver_kind;
     }
     per_step = graph_launches_per_step;
-    for (int i = 0; i < n_steps; ++i) {
+    *static_cast<volatile int*>(host_step) = 0;   // (the stream is idle: prepare_timesteps synchronized it)
+    for (int i = 0; i < n_steps; ++i) {           // the whole loop is enqueued without a host round trip
         if (use_graph) {
             FOLEY_CUDA_OK(cudaGraphLaunch(step_graph, st));
             launches += per_step;
         } else {
             ST_OK(body());
         }
-        if (progress) {
-            FOLEY_CUDA_OK(cudaStreamSynchronize(st));
-            progress(i + 1, user);
-        }
     }
     FOLEY_CUDA_OK(cudaMemcpyAsync(latents, lat_dev, lat_bytes, cudaMemcpyDeviceToDevice, st));
+    if (progress) {
+        // utils.py:247 `pbar.update(1)` per step, on the CALLER's thread: the device publishes the number of completed
+        // steps in mapped host memory and this thread polls it while the GPU keeps running (no per-step synchronize).
+        int reported = 0;
+        for (;;) {
+            const cudaError_t q = cudaStreamQuery(st);
+            const int done = q == cudaSuccess ? n_steps : std::min(n_steps, static_cast<int>(*static_cast<volatile int*>(host_step)));
+            while (reported < done) progress(++reported, user);
+            if (q == cudaSuccess || reported >= n_steps) break;
+            if (q != cudaErrorNotReady) return fail(FOLEY_ERR_CUDA, std::string("denoise: ") + cudaGetErrorString(q));
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
+        }
+    }
     return FOLEY_OK;
 }
 

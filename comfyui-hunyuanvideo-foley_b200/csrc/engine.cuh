@@ -105,6 +105,8 @@ class Engine {
     SolverCall* sol_table = nullptr;
     int sol_table_cap = 0;
     int64_t graph_launches_per_step = 0;
+    int* host_step = nullptr;            // pinned + mapped: steps completed, written by advance_step_kernel, polled by denoise()
+    int* host_step_dev = nullptr;        // its device alias
     int cur_G = 1;
     bool cur_per_sample = false;         // timesteps differ per sample (foley_dit_forward with n_t > 1)
     int *uq_first = nullptr, *uq_src = nullptr, *uq_tok_row = nullptr;   // distinct rows of the sync-token table (set_conditions)

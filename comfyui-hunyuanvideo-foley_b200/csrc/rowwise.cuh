@@ -514,13 +514,16 @@ __global__ void cfg_solver_kernel(const __nv_bfloat16* y, float* lat, __nv_bfloa
 
 // Advances the device-side step counter and the per-group timestep rows (one tiny launch per step so the
 // whole step can be replayed as one CUDA graph).
-__global__ void advance_step_kernel(int* step_ptr, int* trow_of_grp, int G) {
+// `host_step` (mapped pinned host memory, may be null) receives the number of completed steps: the host polls it to
+// drive the progress callback (utils.py:247 pbar.update) without synchronizing the stream after every step.
+__global__ void advance_step_kernel(int* step_ptr, int* trow_of_grp, int G, volatile int* host_step) {
     pdl_wait();
     pdl_trigger();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const int s = *step_ptr + 1;
         *step_ptr = s;
         for (int g = 0; g < G; ++g) trow_of_grp[g] = s;
+        if (host_step) { *host_step = s; __threadfence_system(); }
     }
 }
 

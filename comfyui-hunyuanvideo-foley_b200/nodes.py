@@ -52,8 +52,25 @@ except Exception:  # outside ComfyUI (tests, bench, library use)
         if str(path).endswith(".safetensors"):
             from safetensors.torch import load_file
             return load_file(path, device="cpu")
-        obj = torch.load(path, map_location="cpu", weights_only=False)
+        obj = torch.load(path, map_location="cpu", weights_only=True)   # never un-pickle arbitrary objects
         return obj.get("state_dict", obj) if isinstance(obj, dict) else obj
+
+
+def _check_precision(precision, resolved_dtype=None):
+    """The reference computes in the dtype the loader picks (utils.py:222-239: fp32 without autocast, fp16 / bf16 under
+    autocast).  The engine's arithmetic is bf16 tensor-core GEMMs with fp32 accumulation / residuals / norms: it is the
+    reference's bf16 path.  Any other request is REFUSED rather than silently substituted, unless the user opts in with
+    FOLEY_B200_PRECISION_FALLBACK=bf16 (then `precision` only sets the dtype of the noise draw and of the features, as in
+    the reference, and the DiT still computes in bf16)."""
+    want = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}.get(precision, resolved_dtype)
+    if want in (None, torch.bfloat16):
+        return
+    if os.environ.get("FOLEY_B200_PRECISION_FALLBACK", "").lower() == "bf16":
+        logger.warning("precision=%s requested: computing in bf16 (FOLEY_B200_PRECISION_FALLBACK=bf16)", precision)
+        return
+    raise FoleyError(f"precision={precision!r} (resolved {want}) is not implemented by the B200 engine, which computes the "
+                     "reference's bf16 path (bf16 tensor-core GEMMs, fp32 accumulation, residuals and norms). Choose "
+                     "precision='bf16', or set FOLEY_B200_PRECISION_FALLBACK=bf16 to accept bf16 arithmetic explicitly.")
 
 
 def _foley_files(filter_substr=None):
@@ -97,6 +114,7 @@ class FoleyModel:
         """The Model Loader's work (reference nodes.py:72-126) without a host state dict: header-only dtype sniffing
         (utils.py:492-515), then file -> device through foley_engine_load_safetensors."""
         from . import checkpoint as ck
+        _check_precision(precision)
         header, data_start = ck.read_header(path)
         dts = [(ck.ST_DTYPES.get(e["dtype"]), int(torch.tensor(e["shape"]).prod()) if e["shape"] else 1)
                for e in header.values()]
@@ -104,6 +122,7 @@ class FoleyModel:
         if precision == "auto":
             dtype = ck.detect_major_precision(dts)
             logger.info("Auto precision selected from checkpoint: %s", dtype)
+            _check_precision(precision, dtype)
         qmode = ck.resolve_quantization(quantization, ck.detect_fp8(d for d, _ in dts))
         w = header.get("audio_embedder.proj.weight")
         model_size = "xl" if w is not None and int(w["shape"][0]) == 1408 else "xxl"
@@ -175,7 +194,7 @@ class HunyuanModelLoader:
         return {
             "required": {
                 "model_name": (_foley_files(),),
-                "precision": (["auto", "bf16", "fp16", "fp32"], {"default": "bf16", "tooltip": "The B200 engine computes with bf16 tensor-core GEMMs and fp32 accumulation / residuals for every choice"}),
+                "precision": (["auto", "bf16", "fp16", "fp32"], {"default": "bf16", "tooltip": "The B200 engine computes the reference's bf16 path; fp16 / fp32 are refused unless FOLEY_B200_PRECISION_FALLBACK=bf16 is set"}),
                 "quantization": (["none", "fp8_e4m3fn", "fp8_e5m2", "auto"], {"default": "auto", "tooltip": "Same numbers as the reference's FP8 weight-only storage (weights rounded through FP8 at load); the engine keeps them resident in bf16"}),
             },
         }
@@ -190,9 +209,7 @@ class HunyuanModelLoader:
         model_path = folder_paths.get_full_path("foley", model_name)
         if model_path is None or not os.path.exists(model_path):
             raise FileNotFoundError(f"Hunyuan-Foley checkpoint not found: {model_name}")
-        if precision not in ("auto", "bf16"):
-            logger.warning("precision=%s requested; the B200 engine runs bf16 GEMMs with fp32 accumulation "
-                           "(the choice still sets the dtype of the noise draw and features, as in the reference)", precision)
+        _check_precision(precision)
         if str(model_path).endswith(".safetensors"):
             model = FoleyModel.from_safetensors(model_path, precision, quantization, device=mm.get_torch_device())
         else:   # .pt / .pth checkpoints go through a host state dict like the reference
@@ -202,6 +219,7 @@ class HunyuanModelLoader:
             dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}.get(precision, torch.bfloat16)
             if precision == "auto":
                 dtype = ck.detect_major_precision((v.dtype, v.numel()) for v in tensors)
+                _check_precision(precision, dtype)
             qmode = ck.resolve_quantization(quantization, ck.detect_fp8(v.dtype for v in tensors))
             model = FoleyModel.from_state_dict(state_dict, device=mm.get_torch_device(), dtype=dtype, quantization=qmode)
             del state_dict
@@ -236,7 +254,8 @@ class HunyuanDependenciesLoader:
         # Condition encoders: outside the engine's scope, taken from the reference package when present.
         try:
             from .feature_bridge import load_reference_extractors
-            deps.update(load_reference_extractors(folder_paths.get_full_path("foley", synchformer_name), device))
+            deps.update(load_reference_extractors(folder_paths.get_full_path("foley", synchformer_name), device,
+                                                  load_torch_file))
         except Exception as e:  # noqa: BLE001
             raise FoleyError("The SigLIP2 / Synchformer / CLAP encoders are not part of foley_b200; install the "
                              f"reference node pack next to this one so they can be borrowed ({e})") from e

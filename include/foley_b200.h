@@ -115,8 +115,10 @@ foley_status foley_dit_forward(foley_engine* e, const float* x, const float* t, 
 /* ---- the whole Euler loop (utils.py:203-247 + scheduling_flow_match_discrete.py:210-297) ------
  * latents: [batch, latent_dim, L] f32, in: initial noise, out: final latents.  sigmas: n_steps+1
  * host floats (torch.linspace(1,0,n_steps+1) for shift=1).  guidance: CFG scale (used when
- * n_cond==2).  progress(step, user) is called on the host after each step is enqueued-and-finished
- * when non-NULL (ComfyUI ProgressBar.update, utils.py:247); NULL keeps the loop fully asynchronous. */
+ * n_cond==2).  progress(step, user) (ComfyUI ProgressBar.update, utils.py:247) is called once per finished step on
+ * the CALLING thread when non-NULL: all steps are enqueued first, the device publishes the count of finished steps in
+ * mapped host memory and the call polls it while the GPU keeps running (no per-step stream synchronize); it returns
+ * after the last step was reported.  NULL keeps the call fully asynchronous. */
 typedef void (*foley_progress_fn)(int32_t step, void* user);
 foley_status foley_denoise(foley_engine* e, float* latents, const float* sigmas, int32_t n_steps,
                            float guidance, foley_progress_fn progress, void* user, void* stream);

@@ -440,3 +440,38 @@ def test_safetensors_parser_survives_mutated_files(tmp_path):
             assert 0 <= nb.value <= len(b)
         seen[st] += 1
     assert seen[0] > 0 and seen[1] > 0
+
+
+def test_safetensors_parser_refuses_deep_nesting_without_overflowing_the_stack(tmp_path):
+    """a header whose __metadata__ (or an unknown key of a tensor entry) nests millions of brackets used to
+    recurse once per level and overflow the stack; the parser now refuses anything deeper than 64 levels."""
+    import struct
+    E = load_pkg("engine")
+    lib = E.load_library()
+    entry = '"a":{"dtype":"F32","shape":[1],"data_offsets":[0,4]'
+    for depth, inside_entry in ((2_000_000, False), (500_000, True), (40, False)):
+        nest = "[" * depth + "]" * depth
+        hdr = ('{"__metadata__":' + nest + "," + entry + "}}") if not inside_entry else ("{" + entry + ',"x":' + nest + "}}")
+        hj = hdr.encode()
+        p = str(tmp_path / f"deep{depth}.safetensors")
+        open(p, "wb").write(struct.pack("<Q", len(hj)) + hj + b"\0\0\0\0")
+        n, nb = ctypes.c_int64(), ctypes.c_int64()
+        st = lib.foley_safetensors_probe(p.encode(), ctypes.byref(n), ctypes.byref(nb), None)
+        assert st == (0 if depth <= 64 else 1)
+        if st == 0:
+            assert n.value == 1 and nb.value == 4
+
+
+def test_precision_other_than_bf16_is_refused_not_substituted(monkeypatch):
+    """Reference utils.py:222-239 computes in the loader's dtype; the engine implements the bf16 path only and must
+    say so ('never silently substitute'), with an explicit opt-in for the bf16 fallback."""
+    nodes, E = load_pkg("nodes"), load_pkg("engine")
+    monkeypatch.delenv("FOLEY_B200_PRECISION_FALLBACK", raising=False)
+    nodes._check_precision("bf16")
+    nodes._check_precision("auto", torch.bfloat16)
+    for p, dt in (("fp32", None), ("fp16", None), ("auto", torch.float32), ("auto", torch.float16)):
+        with pytest.raises(E.FoleyError, match="precision"):
+            nodes._check_precision(p, dt)
+    monkeypatch.setenv("FOLEY_B200_PRECISION_FALLBACK", "bf16")
+    nodes._check_precision("fp32")
+    nodes._check_precision("auto", torch.float16)

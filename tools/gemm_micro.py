@@ -20,6 +20,8 @@ ap.add_argument("--splits", type=int, default=0)
 ap.add_argument("--iters", type=int, default=50)
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--all", action="store_true")
+ap.add_argument("--pair", type=int, default=-1, help="-1 default policy, 0 single-CTA tiles, 1 CTA-pair (cta_group::2) tiles")
+ap.add_argument("--sweep", action="store_true", help="every shape x {single, pair} x {full, TMA only, TMA+MMA} at --bn")
 ap.add_argument("--dbg", type=int, default=0, help="bring-up modes: 1 = setup only, 2 = TMA only, 3 = TMA+MMA (no epilogue), 4 = MMA only on a re-used "
                                                        "ring, 8 = full kernel + clock64 timeline of CTA 0")
 a = ap.parse_args()
@@ -40,7 +42,9 @@ SHAPES = {"w13": (C, 3, 2 * Hs, 1, 1), "w2": (Hs, 3, C, 2, 3), "qkv": (C, 1, 3 *
 dev = "cuda"
 
 
-def run(name, bn):
+def run(name, bn, pair=None, dbg=None):
+    pair = a.pair if pair is None else pair
+    dbg = a.dbg if dbg is None else dbg
     K, taps, N, mode, sp = SHAPES[name]
     sp = a.splits or sp
     x = torch.randn(B2, L, K, device=dev).bfloat16()
@@ -52,7 +56,7 @@ def run(name, bn):
     ldo = out.shape[-1]
 
     def launch():
-        s = lib.foley_gemm(x.data_ptr(), 0, B2, L, K, K, L * K, w.data_ptr(), N, taps, -(taps // 2), 1, sp, bn | (a.dbg << 16), mode, 0,
+        s = lib.foley_gemm(x.data_ptr(), 0, B2, L, K, K, L * K, w.data_ptr(), N, taps, -(taps // 2), 1, sp, bn | (dbg << 16) | ((pair + 1) << 20), mode, 0,
                            None, out.data_ptr(), ldo, L * ldo, B2 * L * ldo, None)
         assert s == 0, lib.foley_last_error()
 
@@ -67,8 +71,10 @@ def run(name, bn):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / a.iters
     fl = 2.0 * B2 * L * K * taps * N
-    print(f"{name:5s} K={K}x{taps} N={N} bn={bn} splits={sp}: {us:7.1f} us  {fl / us / 1e6:7.1f} TFLOP/s", flush=True)
-    if a.dbg == 8:
+    kb = K * taps // 64 // sp
+    print(f"{name:5s} K={K}x{taps} N={N} bn={bn} splits={sp} pair={pair} dbg={dbg}: {us:7.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  "
+          f"({us / kb:.3f} us per k-block of {kb})", flush=True)
+    if dbg == 8:
         t = (ctypes.c_uint64 * 16)()
         lib.foley_debug_times(t)
         t = list(t)
@@ -83,7 +89,12 @@ def run(name, bn):
             print(f"        {nm:28s} {(m - t[0]) / ghz:8.0f}")
 
 
-if a.all:
+if a.sweep:
+    for n in ("w13", "w2", "qkv", "fc1", "fc2", "lin1"):
+        for pair in (0, 1):
+            for dbg in (0, 2, 3):
+                run(n, a.bn, pair, dbg)
+elif a.all:
     for n in SHAPES:
         for bn in (128, 256):
             run(n, bn)
