@@ -19,6 +19,10 @@
 #ifndef FOLEY_GEMM_TWO_PRODUCERS
 #define FOLEY_GEMM_TWO_PRODUCERS 1   // 0: warp 0 issues both loads of a k-block (A/B switch for the round-2 bisect of the w1|w3 shape)
 #endif
+#ifndef FOLEY_PAIR_DIRECT
+#define FOLEY_PAIR_DIRECT 1   // CTA-pair tiles: both CTAs' TMA loads complete on the LEADER's full barrier (cta_group::2 TMA form; the
+                              // leader expects the pair's bytes) instead of the peer forwarding "stage landed" with a remote arrive
+#endif
 #ifndef FOLEY_SWIGLU_STAGED
 #define FOLEY_SWIGLU_STAGED 0     // 1: SwiGLU tiles also leave through the staging buffer (measured 0.8 us slower per tile)
 #endif
@@ -141,12 +145,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     // Each CTA's loads complete on its OWN full barrier (two arrivals per phase: the weight producer's and the
     // activation producer's expect_tx); in pair mode the peer forwards "stage landed" to the leader with one remote
     // arrive per stage (remote complete_tx from TMA, the cta_group::2 TMA form, measured slower here).
+    constexpr bool kDirect = kPair && FOLEY_PAIR_DIRECT && FOLEY_GEMM_TWO_PRODUCERS;
+    const uint32_t lead_full = kDirect ? mapa_u32(smem_u32(full_bar), 0) : 0;   // the leader's full barriers (shared::cluster)
     auto load_b = [&](int s, int kb) {
-        mbar_expect_tx(&full_bar[s], Cfg::B_BYTES);
-        tma_load_3d(smem_b + s * Cfg::B_BYTES, &tm_b, &full_bar[s], kb * Cfg::BK,
-                    n0 + static_cast<int>(pair_rank) * Cfg::B_ROWS, 0);   // rank-3 map; pair: this CTA's half
+        if constexpr (kDirect) {
+            if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::B_BYTES);   // both halves of the B tile land on this barrier
+            tma_load_3d_pair(smem_b + s * Cfg::B_BYTES, &tm_b, lead_full + s * 8, kb * Cfg::BK,
+                             n0 + static_cast<int>(pair_rank) * Cfg::B_ROWS, 0);
+        } else {
+            mbar_expect_tx(&full_bar[s], Cfg::B_BYTES);
+            tma_load_3d(smem_b + s * Cfg::B_BYTES, &tm_b, &full_bar[s], kb * Cfg::BK,
+                        n0 + static_cast<int>(pair_rank) * Cfg::B_ROWS, 0);   // rank-3 map; pair: this CTA's half
+        }
+    };
+    auto load_a = [&](int s, int kcol, int arow) {
+        if constexpr (kDirect) {
+            if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::A_BYTES);
+            tma_load_3d_pair(smem_a + s * Cfg::A_BYTES, &tm_a, lead_full + s * 8, kcol, arow, batch);
+        } else {
+            mbar_expect_tx(&full_bar[s], Cfg::A_BYTES);
+            tma_load_3d(smem_a + s * Cfg::A_BYTES, &tm_a, &full_bar[s], kcol, arow, batch);
+        }
     };
     const int pre = g.dbg_stop == 1 ? 0 : (num_kb < Cfg::STAGES ? num_kb : Cfg::STAGES);
+    // direct pair mode: the peer's loads signal the LEADER's barriers, which exist only after the cluster sync below
+    const int pre_early = (kDirect && !leader) ? 0 : pre;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
@@ -162,7 +185,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // Weights do not depend on the previous kernel (programmatic dependent launch) nor on the TMEM allocation
         // going on in warp 1: fill the ring with B tiles right away so the weight stream's latency hides under the
         // rest of the prologue and under the predecessor kernel's tail.
-        for (int i = 0; i < pre; ++i) load_b(i, kb_begin + i);
+        for (int i = 0; i < pre_early; ++i) load_b(i, kb_begin + i);
     } else if (warp == 1) {
         if constexpr (kPair) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr_smem);
         else tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
@@ -180,10 +203,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // ------------------------------------------------------------- TMA producer: weight tiles past the first ring pass
 #if FOLEY_GEMM_TWO_PRODUCERS
         if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 1;   // round r >= 1 waits for the consumer's release of round r-1: parity (r & 1) ^ 1
-            for (int i = pre; i < (g.dbg_stop == 4 ? 0 : num_kb); ++i) {
-                if (!mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + i)) break;
+            int s = pre_early == Cfg::STAGES ? 0 : pre_early;
+            uint32_t ph = pre_early == Cfg::STAGES ? 1 : 0;   // round r >= 1 waits for the consumer's release of round r-1: parity (r & 1) ^ 1
+            for (int i = pre_early; i < (g.dbg_stop == 4 ? 0 : num_kb); ++i) {
+                if (i >= Cfg::STAGES) { if (!mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + i)) break; }
                 load_b(s, kb_begin + i);
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
             }
@@ -220,15 +243,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             if (tprobe) g_foley_times[2] = clock64();
             for (int i = 0; i < (g.dbg_stop == 4 ? pre : num_kb); ++i) {
                 if (i >= Cfg::STAGES) { if (!mbar_wait(&empty_bar[s], ph ^ 1, 0x180 + i)) break; }
-                mbar_expect_tx(&full_bar[s], Cfg::A_BYTES);
-                tma_load_3d(smem_a + s * Cfg::A_BYTES, &tm_a, &full_bar[s], kk * Cfg::BK, arow, batch);
+                load_a(s, kk * Cfg::BK, arow);
                 if (++kk == g.kb_per_tap) { kk = 0; arow += g.tap_stride; }
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------- MMA issuer (one thread; pair: leader CTA only)
-        if (lane == 0 && !leader) {
+        if (lane == 0 && !leader && !kDirect) {
             // peer CTA of a pair: forward each landed stage to the leader
             int s = 0;
             uint32_t ph = 0;
@@ -247,7 +269,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 if (s == 0) ph ^= 1;
                 if (g.dbg_stop != 4 || i < pre) {   // dbg 4: MMA-only rate, the first ring pass is re-used without reloading
                 if (!mbar_wait(&full_bar[s], ph, 0x200 + i)) break;
-                if constexpr (kPair) { if (!mbar_wait(&peer_ready[s], ph, 0x500 + i)) break; }
+                if constexpr (kPair && !kDirect) { if (!mbar_wait(&peer_ready[s], ph, 0x500 + i)) break; }
                 }
                 tc_fence_after();
                 if (tprobe && i == 0) g_foley_times[3] = clock64();

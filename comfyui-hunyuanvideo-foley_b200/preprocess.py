@@ -66,7 +66,10 @@ def preprocess_video(image, duration, frame_rate, device):
     # only the frames that are actually picked travel to the device
     used = torch.unique(torch.cat([idx8, idx25]))
     remap = {int(u): i for i, u in enumerate(used.tolist())}
-    frames = image.index_select(0, used.to(image.device)).to(device, torch.float32)
+    if used.numel() == total_input_frames:   # every frame is picked (fps <= 8..25): no host-side gather, one (async) upload
+        frames = image.to(device, torch.float32, non_blocking=True)
+    else:
+        frames = image.index_select(0, used.to(image.device)).to(device, torch.float32)
     H, W = frames.shape[1], frames.shape[2]
     nh, nw = resized_size_short_side(H, W, SYNC_SIZE)
     top, left = center_crop_offsets(nh, nw, SYNC_SIZE, SYNC_SIZE)

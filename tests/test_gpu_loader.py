@@ -73,9 +73,10 @@ def test_fp8_weight_storage_matches_oracle_and_prequantised_checkpoint(tmp_path,
         assert torch.equal(got2, got), storage
 
 
-def test_model_loader_from_safetensors(tmp_path):
+def test_model_loader_from_safetensors(tmp_path, monkeypatch):
     """FoleyModel.from_safetensors: header-only precision / fp8 detection, host copies of the empty-feature rows, and a
-    working engine; `quantization=auto` on B200 means e4m3fn storage, as in the reference (nodes.py:108-119)."""
+    working engine; `quantization=auto` on B200 means e4m3fn storage, as in the reference (nodes.py:108-119).
+    precision=fp32 is REFUSED (the engine is the reference's bf16 path) unless the user opts into bf16 arithmetic."""
     nodes, cfgmod, ck = load_pkg("nodes"), load_pkg("config"), load_pkg("checkpoint")
     c = W.model_config("tiny")
     sd = {k: v.bfloat16() for k, v in W.synth_dit_state_dict(c, seed=0).items()}
@@ -85,6 +86,10 @@ def test_model_loader_from_safetensors(tmp_path):
     for k in ("hidden_size", "num_heads", "depth_triple_blocks", "depth_single_blocks"):
         cfg.model_config.model_kwargs[k] = c[k]
     m_auto = nodes.FoleyModel.from_safetensors(path, precision="auto", quantization="auto", cfg=cfg)
+    E = load_pkg("engine")
+    with pytest.raises(E.FoleyError, match="not implemented by the B200 engine"):
+        nodes.FoleyModel.from_safetensors(path, precision="fp32", quantization="none", cfg=cfg)
+    monkeypatch.setenv("FOLEY_B200_PRECISION_FALLBACK", "bf16")
     m_none = nodes.FoleyModel.from_safetensors(path, precision="fp32", quantization="none", cfg=cfg)
     assert m_auto.dtype == torch.bfloat16 and m_none.dtype == torch.float32
     assert torch.equal(m_auto.empty_clip_feat, sd["empty_clip_feat"])
