@@ -2,6 +2,8 @@
 #include <new>
 
 #include "common.cuh"
+#include "attention.cuh"
+#include "attention_tc.cuh"
 #include "engine.cuh"
 #include "gemm_host.cuh"
 #include "preprocess.cuh"
@@ -44,6 +46,68 @@ extern "C" foley_status foley_gemm(const void* a, int32_t dtype, int64_t batch, 
     L.epi.out_batch_stride = out_batch_stride; L.epi.split_stride = split_stride;
     std::string err;
     if (!launch_gemm(L, static_cast<cudaStream_t>(stream), &err)) return fail(FOLEY_ERR_CUDA, err);
+    return FOLEY_OK;
+}
+
+static AttOperand to_att_operand(const foley_attn_src& s, int heads) {
+    AttOperand o;
+    o.ptr = static_cast<const __nv_bfloat16*>(s.ptr);
+    o.batch_stride = s.batch_stride; o.head_stride = s.head_stride; o.row_stride = s.row_stride;
+    o.rows = s.rows; o.heads = heads; o.batch = s.batch;
+    return o;
+}
+static AttNorm to_att_norm(const foley_attn_src& s) {
+    AttNorm n;
+    n.rows0 = s.rows0;
+    for (int i = 0; i < 2; ++i) {
+        n.w[i] = static_cast<const __nv_bfloat16*>(s.norm_w[i]);
+        n.rope[i] = reinterpret_cast<const float2*>(s.rope[i]);
+    }
+    return n;
+}
+
+extern "C" foley_status foley_attention(const foley_attn_args* g, void* stream) {
+    if (!g || !g->out) return fail(FOLEY_ERR_INVALID, "foley_attention: null pointer");
+    if (g->batch < 1 || g->heads < 1) return fail(FOLEY_ERR_INVALID, "foley_attention: bad shape");
+    for (const foley_attn_src* s : {&g->q, &g->k, &g->v}) {
+        if (!s->ptr || s->rows < 1 || s->batch < 1 || s->rows0 < 0 || s->rows0 > s->rows)
+            return fail(FOLEY_ERR_INVALID, "foley_attention: bad operand");
+        if ((reinterpret_cast<uintptr_t>(s->ptr) & 15) || (s->batch_stride | s->head_stride | s->row_stride) % 8)
+            return fail(FOLEY_ERR_INVALID, "foley_attention: operands must be 16-byte aligned (pointer and strides)");
+        for (int i = 0; i < 2; ++i)
+            if (s->norm_w[i] && !s->rope[i]) return fail(FOLEY_ERR_INVALID, "foley_attention: norm_w needs the (cos, sin) table");
+    }
+    if (g->k.rows != g->v.rows) return fail(FOLEY_ERR_INVALID, "foley_attention: k and v must have the same length");
+    if (g->v.norm_w[0] || g->v.norm_w[1]) return fail(FOLEY_ERR_INVALID, "foley_attention: v takes no norm");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g->impl == 1) {
+        if (g->q.norm_w[0] || g->q.norm_w[1] || g->k.norm_w[0] || g->k.norm_w[1] || g->q.row_stride != 128 ||
+            g->k.row_stride != 128 || g->v.row_stride != 128)
+            return fail(FOLEY_ERR_UNSUPPORTED, "foley_attention: impl 1 takes prepared [B,H,S,128] inputs");
+        AttnArgs a;
+        a.q = static_cast<const __nv_bfloat16*>(g->q.ptr); a.k = static_cast<const __nv_bfloat16*>(g->k.ptr);
+        a.v = static_cast<const __nv_bfloat16*>(g->v.ptr); a.o = static_cast<__nv_bfloat16*>(g->out);
+        a.H = g->heads; a.Sq = g->q.rows; a.Sk = g->k.rows;
+        a.q_batch_stride = g->q.batch_stride; a.q_head_stride = g->q.head_stride;
+        a.kv_batch_stride = g->k.batch_stride; a.kv_head_stride = g->k.head_stride;
+        a.o_batch_stride = g->out_batch_stride; a.kv_batch_map = g->kv_batch_map;
+        a.scale_log2 = g->scale * 1.4426950408889634f;
+        { static bool once = false; if (!once) { FOLEY_CUDA_OK(cudaFuncSetAttribute(attention_kernel<8, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<8, 3, 2>::SMEM)); once = true; } }
+        dim3 grid((a.Sq + 63) / 64, g->heads, g->batch);
+        FOLEY_CUDA_OK(launch_k(attention_kernel<8, 3, 2>, grid, dim3(256), AttCfg<8, 3, 2>::SMEM, st, a));
+        return FOLEY_OK;
+    }
+    AttTcArgs a;
+    a.qn = to_att_norm(g->q); a.kn = to_att_norm(g->k);
+    a.o = static_cast<__nv_bfloat16*>(g->out); a.o_batch_stride = g->out_batch_stride;
+    a.H = g->heads; a.Sq = g->q.rows; a.Sk = g->k.rows; a.kv_batch_map = g->kv_batch_map;
+    a.scale_log2 = g->scale * 1.4426950408889634f; a.norm_kind = g->norm_kind; a.eps = g->eps;
+    a.probe_chunk = g->dbg[0] - 1;
+    { static bool once = false; if (!once) { FOLEY_CUDA_OK(attention_tc_init()); once = true; } }
+    std::string err;
+    if (!launch_attention_tc(to_att_operand(g->q, g->heads), to_att_operand(g->k, g->heads), to_att_operand(g->v, g->heads), a,
+                             g->batch, st, &err))
+        return fail(FOLEY_ERR_CUDA, err);
     return FOLEY_OK;
 }
 

@@ -105,6 +105,9 @@ foley_status Engine::create(const foley_config* c, int dev) {
         FOLEY_CUDA_OK(cudaFuncSetAttribute(attention_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<4, 4>::SMEM));
         FOLEY_CUDA_OK(cudaFuncSetAttribute(attention_kernel<8, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<8, 3, 2>::SMEM));
         if (const char* e = getenv("FOLEY_ATT_KVSPLIT")) att_kv_split = atoi(e) != 0;
+        if (const char* e = getenv("FOLEY_ATT_TC")) att_tc = atoi(e);
+        if (const char* e = getenv("FOLEY_ATT_FUSED")) att_fused = atoi(e) != 0;
+        FOLEY_CUDA_OK(attention_tc_init());
         FOLEY_CUDA_OK(cudaFuncSetAttribute(attention_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<8, 3>::SMEM));
     }
     triple.resize(NT);
@@ -407,6 +410,10 @@ foley_status Engine::alloc_plan(int B, int U, int L, int Lv, int S, int T) {
     ST_OK(palloc(&rope_av_v_sin, static_cast<size_t>(Lv) * 128));
     ST_OK(palloc(&rope_plain_cos, static_cast<size_t>(Pmax) * 128));
     ST_OK(palloc(&rope_plain_sin, static_cast<size_t>(Pmax) * 128));
+    ST_OK(palloc(&rope2_av_a, static_cast<size_t>(L) * 64));
+    ST_OK(palloc(&rope2_av_v, static_cast<size_t>(Lv) * 64));
+    ST_OK(palloc(&rope2_plain, static_cast<size_t>(Pmax) * 64));
+    ST_OK(palloc(&qkv_j, B2 * Sj * 3 * C));
     ST_OK(palloc(&grp_of_sample, B2));
     ST_OK(palloc(&trow_of_grp, B2));
     ST_OK(palloc(&cond_of_grp, B2));
@@ -642,16 +649,21 @@ foley_status Engine::set_conditions(const void* clip, const void* sync, const vo
         for (int j = 0; j < Lv; ++j) pv[j] = (L == Lv) ? 2 * j + 1 : 2 * pick[j] + 1;
         for (size_t i = 0; i < pp.size(); ++i) pp[i] = static_cast<int>(i);
         std::vector<float> c, s;
-        auto up = [&](const std::vector<int>& pos, float* dc, float* ds) -> foley_status {
+        std::vector<float2> cs2;
+        auto up = [&](const std::vector<int>& pos, float* dc, float* ds, float2* d2) -> foley_status {
             host_rope_table(pos, cfg.rope_theta, &c, &s);
+            cs2.resize(pos.size() * 64);    // the same values, one (cos, sin) per rotation pair
+            for (size_t p = 0; p < pos.size(); ++p)
+                for (int k = 0; k < 64; ++k) cs2[p * 64 + k] = make_float2(c[p * 128 + 2 * k], s[p * 128 + 2 * k]);
             FOLEY_CUDA_OK(cudaMemcpyAsync(dc, c.data(), c.size() * 4, cudaMemcpyHostToDevice, st));
             FOLEY_CUDA_OK(cudaMemcpyAsync(ds, s.data(), s.size() * 4, cudaMemcpyHostToDevice, st));
+            FOLEY_CUDA_OK(cudaMemcpyAsync(d2, cs2.data(), cs2.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
             FOLEY_CUDA_OK(cudaStreamSynchronize(st));
             return FOLEY_OK;
         };
-        ST_OK(up(pa, rope_av_a_cos, rope_av_a_sin));
-        ST_OK(up(pv, rope_av_v_cos, rope_av_v_sin));
-        ST_OK(up(pp, rope_plain_cos, rope_plain_sin));
+        ST_OK(up(pa, rope_av_a_cos, rope_av_a_sin, rope2_av_a));
+        ST_OK(up(pv, rope_av_v_cos, rope_av_v_sin, rope2_av_v));
+        ST_OK(up(pp, rope_plain_cos, rope_plain_sin, rope2_plain));
         tables_ready = true;
     }
     // ---- text branch: cond_in, then K/V of every triple block at once (step-invariant, hifi_foley.py:289-308)
@@ -773,6 +785,21 @@ foley_status Engine::step(cudaStream_t st) {
         a.kv_batch_map = cross ? cond_of_grp : nullptr;
         a.grp_of_sample = cross ? grp_of_sample : nullptr;
         a.scale_log2 = 1.4426950408889634f / sqrtf(128.0f);
+        if (att_tc > 0 || (att_tc < 0 && Sk > ATC_CK)) {   // prepared [B,H,S,128] operands on the tcgen05 kernel
+            AttOperand oq, ok_, ov;
+            oq.ptr = q; oq.batch_stride = a.q_batch_stride; oq.head_stride = a.q_head_stride; oq.row_stride = 128;
+            oq.rows = Sq; oq.heads = H; oq.batch = B2;
+            ok_.ptr = k; ok_.batch_stride = kv_bs; ok_.head_stride = kv_hs; ok_.row_stride = 128;
+            ok_.rows = Sk; ok_.heads = H; ok_.batch = cross ? p.U : B2;
+            ov = ok_; ov.ptr = v;
+            AttTcArgs t;
+            t.o = attn_out; t.o_batch_stride = a.o_batch_stride; t.H = H; t.Sq = Sq; t.Sk = Sk;
+            t.kv_batch_map = a.kv_batch_map; t.grp_of_sample = a.grp_of_sample; t.scale_log2 = a.scale_log2;
+            std::string err;
+            if (!launch_attention_tc(oq, ok_, ov, t, B2, st, &err)) return fail(FOLEY_ERR_CUDA, err);
+            ++launches;
+            return FOLEY_OK;
+        }
         const long long ctas64 = static_cast<long long>((Sq + 63) / 64) * H * B2;
         if (ctas64 > 2LL * num_sms) {
             dim3 grid((Sq + 127) / 128, H, B2);
@@ -855,6 +882,27 @@ foley_status Engine::step(cudaStream_t st) {
         return FOLEY_OK;
     };
     const int RV = B2 * Lv;   // visual rows, flattened (no token conv on this stream, so samples need no halo)
+    // Fused attention (attention_tc.cuh): the projection GEMMs of both streams write bf16 rows into ONE [B2][Lv + L][n]
+    // buffer (visual rows first) and the attention kernel normalises / rotates them while loading its operands — no
+    // qk_norm_rope_kernel launch, no [B,H,S,128] round trip.  Needs all keys resident (<= 320), else the prepared path.
+    const bool fused = att_tc != 0 && att_fused && Sj <= ATC_CK && !(debug_skip & 3);
+    auto fused_proj = [&](cudaStream_t s_, const bf16* A, int rows, const LinearW& W, int n_cols, int row_off) -> foley_status {
+        GemmEpi e = bf(qkv_j + static_cast<long long>(row_off) * n_cols, n_cols, W.b, 0);
+        e.out_batch_stride = static_cast<long long>(Sj) * n_cols;
+        return gemm(s_, A, rows, B2, C, static_cast<long long>(rows) * C, W, 0, n_cols, e, 1, pick_bn(rows, B2, n_cols, C / 64));
+    };
+    auto att_operand = [&](const bf16* ptr, long long row_stride, int rows, int batch, long long batch_stride, long long head_stride) {
+        AttOperand o; o.ptr = ptr; o.row_stride = row_stride; o.rows = rows; o.batch = batch; o.batch_stride = batch_stride;
+        o.head_stride = head_stride; o.heads = H; return o;
+    };
+    auto fused_attn = [&](const AttOperand& oq, const AttOperand& ok_, const AttOperand& ov, AttTcArgs t) -> foley_status {
+        t.o = attn_out; t.o_batch_stride = static_cast<long long>(oq.rows) * C; t.H = H; t.Sq = oq.rows; t.Sk = ok_.rows;
+        t.scale_log2 = 1.4426950408889634f / sqrtf(128.0f);
+        std::string err;
+        if (!launch_attention_tc(oq, ok_, ov, t, B2, st, &err)) return fail(FOLEY_ERR_CUDA, err);
+        ++launches;
+        return FOLEY_OK;
+    };
     // ---- embed: audio0 = audio_embedder(x) + a_sync (fp32), v_cond0; LN+modulate for block 0
     {
         CombineArgs ca;
@@ -871,6 +919,20 @@ foley_status Engine::step(cudaStream_t st) {
     for (int i = 0; i < ((debug_skip >> 9) & 1 ? 0 : NT); ++i) {
         const TripleW& w = triple[i];
         // -- joint self attention
+        if (fused) {
+            ST_OK(fused_proj(st, h_a, L, w.qkv[0], 3 * C, Lv));
+            ST_OK(fused_proj(sv, h_v, Lv, w.qkv[1], 3 * C, 0));
+            ST_OK(join());
+            const long long rs = 3LL * C, bs = static_cast<long long>(Sj) * rs;
+            AttTcArgs t;
+            t.norm_kind = 0; t.eps = 1e-6f;
+            t.qn.rows0 = t.kn.rows0 = Lv;
+            t.qn.w[0] = w.self_q_norm[1]; t.qn.w[1] = w.self_q_norm[0];
+            t.kn.w[0] = w.self_k_norm[1]; t.kn.w[1] = w.self_k_norm[0];
+            t.qn.rope[0] = t.kn.rope[0] = rope2_av_v; t.qn.rope[1] = t.kn.rope[1] = rope2_av_a;
+            ST_OK(fused_attn(att_operand(qkv_j, rs, Sj, B2, bs, 128), att_operand(qkv_j + C, rs, Sj, B2, bs, 128),
+                             att_operand(qkv_j + 2 * C, rs, Sj, B2, bs, 128), t));
+        } else {
         QkvArgs qa_joint, qv_joint;
         ST_OK(qkv_gemm(st, h_a, L, B2, w.qkv[0], 3 * C, part_a, C, qkv_a, &qa_joint));
         ST_OK(qkv_gemm(sv, h_v, RV, 1, w.qkv[1], 3 * C, part_v, 3 * C, qkv_v, &qv_joint));
@@ -889,6 +951,7 @@ foley_status Engine::step(cudaStream_t st) {
         }
         ST_OK(join());
         ST_OK(attn(Qj, Kj, Vj, Sj, Sj, jb, jh, false));
+        }
         ST_OK(fork());
         {
             CombineArgs ca;
@@ -901,6 +964,21 @@ foley_status Engine::step(cudaStream_t st) {
             ST_OK(proj_combine(sv, attn_out, Lv, B2, C, jb, w.self_proj[1], part_v, cv));
         }
         // -- cross attention to text
+        const long long tblk = static_cast<long long>(p.U) * T * C;
+        if (fused && T <= ATC_CK) {
+            ST_OK(fused_proj(st, h_a, L, w.cross_q[0], C, Lv));
+            ST_OK(fused_proj(sv, h_v, Lv, w.cross_q[1], C, 0));
+            ST_OK(join());
+            AttTcArgs t;
+            t.norm_kind = 0; t.eps = 1e-6f;
+            t.qn.rows0 = Lv;
+            t.qn.w[0] = w.cross_q_norm[1]; t.qn.w[1] = w.cross_q_norm[0];
+            t.qn.rope[0] = t.qn.rope[1] = rope2_plain;
+            t.kv_batch_map = cond_of_grp; t.grp_of_sample = grp_of_sample;
+            const long long tb = static_cast<long long>(T) * C, th = static_cast<long long>(T) * 128;
+            ST_OK(fused_attn(att_operand(qkv_j, C, Sj, B2, static_cast<long long>(Sj) * C, 128),
+                             att_operand(text_k + i * tblk, 128, T, p.U, tb, th), att_operand(text_v + i * tblk, 128, T, p.U, tb, th), t));
+        } else {
         QkvArgs qa_cross, qv_cross;
         ST_OK(qkv_gemm(st, h_a, L, B2, w.cross_q[0], C, part_a, C, qkv_a, &qa_cross));
         ST_OK(qkv_gemm(sv, h_v, RV, 1, w.cross_q[1], C, part_v, 3 * C, qkv_v, &qv_cross));
@@ -913,10 +991,10 @@ foley_status Engine::step(cudaStream_t st) {
             ST_OK(qknorm_on(s == 0 ? st : sv, q));
         }
         ST_OK(join());
+        ST_OK(attn(Qj, text_k + i * tblk, text_v + i * tblk, Sj, T, static_cast<long long>(T) * C,
+                   static_cast<long long>(T) * 128, true));
+        }
         {
-            const long long blk = static_cast<long long>(p.U) * T * C;
-            ST_OK(attn(Qj, text_k + i * blk, text_v + i * blk, Sj, T, static_cast<long long>(T) * C,
-                       static_cast<long long>(T) * 128, true));
             ST_OK(fork());
             CombineArgs ca;
             ca.bias = w.cross_proj[0].b; ca.gate = tmod(i, 0); ca.gate_chunk = 5; ca.x = audio; ca.h = h_a; ca.eps = 1e-6f;
@@ -951,7 +1029,18 @@ foley_status Engine::step(cudaStream_t st) {
     for (int j = 0; j < ((debug_skip >> 10) & 1 ? 0 : NS); ++j) {
         const SingleW& w = single[j];
         skip_gemm_once = (debug_skip >> 5) & 1;
-        {
+        if (fused) {
+            GemmEpi e = bf(qkv_j, 3 * C, w.qkv.b, 0);
+            ST_OK(gemm(st, h_a, L, B2, C, sb, w.qkv, 0, 3 * C, e, 1, pick_bn(L, B2, 3 * C, C / 64)));
+            const long long rs = 3LL * C, bs = static_cast<long long>(L) * rs;
+            AttTcArgs t;
+            t.norm_kind = 1; t.eps = cfg.single_rms_eps;
+            t.qn.rows0 = t.kn.rows0 = L;
+            t.qn.w[0] = w.q_norm; t.kn.w[0] = w.k_norm;
+            t.qn.rope[0] = t.kn.rope[0] = rope2_plain;
+            ST_OK(fused_attn(att_operand(qkv_j, rs, L, B2, bs, 128), att_operand(qkv_j + C, rs, L, B2, bs, 128),
+                             att_operand(qkv_j + 2 * C, rs, L, B2, bs, 128), t));
+        } else {
             QkvArgs q;
             ST_OK(qkv_gemm(st, h_a, L, B2, w.qkv, 3 * C, part_a, C, qkv_a, &q));
             q.n_parts = 3; q.H = H; q.L = L; q.rows_total = B2 * L;
@@ -963,8 +1052,8 @@ foley_status Engine::step(cudaStream_t st) {
                 q.part[pz].seq_offset = 0; q.part[pz].norm_w = norms[pz]; q.part[pz].src_col = pz * C;
             }
             ST_OK(qknorm_on(st, q));
+            ST_OK(attn(Qj, Kj, Vj, L, L, sb, sh, false));
         }
-        ST_OK(attn(Qj, Kj, Vj, L, L, sb, sh, false));
         {
             CombineArgs ca;
             ca.bias = w.linear1.b; ca.gate = smod(j); ca.gate_chunk = 2; ca.x = audio; ca.h = h_a; ca.eps = 1e-5f;

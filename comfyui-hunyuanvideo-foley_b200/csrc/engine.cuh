@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "gemm_host.cuh"
 #include "rowwise.cuh"
+#include "attention_tc.cuh"
 
 namespace foley {
 
@@ -85,6 +86,8 @@ class Engine {
     bf16 *a_sync = nullptr, *vcond0 = nullptr, *text_k = nullptr, *text_v = nullptr;
     float *rope_av_a_cos = nullptr, *rope_av_a_sin = nullptr, *rope_av_v_cos = nullptr, *rope_av_v_sin = nullptr;
     float *rope_plain_cos = nullptr, *rope_plain_sin = nullptr;
+    float2 *rope2_av_a = nullptr, *rope2_av_v = nullptr, *rope2_plain = nullptr;   // the same tables as [rows][64] (cos, sin) pairs (attention_tc.cuh)
+    bf16* qkv_j = nullptr;                // [B2][Lv + L][3C]: QKV (or cross-Q, [..][C]) of both streams, visual rows first, read by the fused attention
     int *grp_of_sample = nullptr, *trow_of_grp = nullptr, *cond_of_grp = nullptr, *step_dev = nullptr;
     float *sigmas_dev = nullptr, *t_dev = nullptr;
     bf16 *vec_all = nullptr, *mod_triple = nullptr;
@@ -118,6 +121,15 @@ class Engine {
     cudaEvent_t ev_mod = nullptr;
     bool qkv_split = true;               // audio QKV / cross-Q GEMMs may split K (partials summed by the q/k-norm kernel)
     bool att_kv_split = true;            // small attention grids: in-CTA split-KV variant (FOLEY_ATT_KVSPLIT=0 disables)
+    // Attention kernel policy.  att_tc: -1 (default) = tcgen05 / TMEM kernel (attention_tc.cuh) for sequences of more than
+    // 320 keys (measured 1.6-1.9x the mma.sync kernel at 1500 / 1740 keys), the mma.sync kernel below that (a 5 s clip:
+    // the tcgen05 kernel alone is as fast, 9.6 vs 9.8 us, but it holds a whole SM — 195 KB of shared memory, all of TMEM —
+    // so its neighbours in the graph no longer overlap with it: step 4.24 vs 4.06 ms); FOLEY_ATT_TC=1 / 0 forces one kernel.
+    // att_fused (FOLEY_ATT_FUSED=1, off by default): q/k-norm + RoPE inside the tcgen05 kernel's operand load for
+    // sequences of <= 320 keys; correct (tests) but the norm work is then concentrated on the 44-66 SMs of the attention
+    // grid and repeated per query tile: +7 us per call, step 4.51 ms.
+    int att_tc = -1;
+    bool att_fused = false;
     bool mod_on_branch = false;          // measured: no gain (the GEMM saturates the SMs either way)
     // planner cost model (us): a k-block costs the same for every tile width (one tcgen05.mma ~150 cycles whatever N), so
     // wide tiles + more K-splits win whenever they fit the SMs (measured: tools/gemm_micro.py --dbg 4, FOLEY_PLAN sweeps)

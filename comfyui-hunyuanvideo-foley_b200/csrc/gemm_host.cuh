@@ -351,6 +351,9 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
                                        : launch_gemm_inst<128, false>(ma, mb, mc, args, grid, stream);
         else if (L.bn == 256) e = pair ? launch_gemm_inst<256, false, true>(ma, mb, mc, args, grid, stream)
                                        : launch_gemm_inst<256, false>(ma, mb, mc, args, grid, stream);
+        // (in-between widths that put one tile on every SM — 208 columns x 148 CTAs for the w1|w3 shape, 192 for fc1 — were
+        //  measured in round 2: no gain, 29.5 vs 28.9 us; the mainloop is bound by the aggregate L2 -> shared-memory copy
+        //  rate of all CTAs (~17.5 TB/s), not by the MMA width: profiles/r02_experiments.md)
         else { if (err) *err = "unsupported BN"; return false; }
     } else {
         if (L.bn == 64) e = launch_gemm_inst<64, true>(ma, mb, mc, args, grid, stream);

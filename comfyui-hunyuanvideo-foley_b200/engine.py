@@ -27,6 +27,18 @@ class _Config(ctypes.Structure):
                [(n, c_int32) for n in ("max_batch", "max_seconds", "with_dac")]
 
 
+class _AttnSrc(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("batch_stride", c_int64), ("head_stride", c_int64), ("row_stride", c_int64),
+                ("rows", c_int32), ("rows0", c_int32), ("batch", c_int32), ("reserved", c_int32),
+                ("norm_w", c_void_p * 2), ("rope", c_void_p * 2)]
+
+
+class _AttnArgs(ctypes.Structure):
+    _fields_ = [("q", _AttnSrc), ("k", _AttnSrc), ("v", _AttnSrc), ("out", c_void_p), ("out_batch_stride", c_int64),
+                ("batch", c_int32), ("heads", c_int32), ("kv_batch_map", c_void_p),
+                ("scale", c_float), ("norm_kind", c_int32), ("eps", c_float), ("impl", c_int32), ("dbg", c_int32 * 4)]
+
+
 PROGRESS_FN = ctypes.CFUNCTYPE(None, c_int32, c_void_p)
 _lib = None
 
@@ -69,6 +81,7 @@ def load_library(path=None):
     lib.foley_debug_read.argtypes = [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int64)]
     lib.foley_debug_flags.argtypes = [POINTER(ctypes.c_uint32)]
     lib.foley_engine_set_option.argtypes = [c_void_p, c_char_p, c_int64]
+    lib.foley_attention.argtypes = [POINTER(_AttnArgs), c_void_p]
     _lib = lib
     return lib
 
@@ -252,3 +265,33 @@ class FoleyEngine:
         buf = (ctypes.c_uint32 * 4)()
         _check(self.lib.foley_debug_flags(buf))
         return list(buf)
+
+
+def attention(q, k, v, out, heads, kv_batch_map=None, scale=None, norm_kind=0, eps=1e-6, impl=0, dbg=(0, 0, 0, 0), stream=None):
+    """foley_attention (include/foley_b200.h): softmax(Q K^T * scale) V for head_dim 128 on the tcgen05 kernel, with the
+    q/k RMSNorm + RoPE optionally folded into the operand load.  q / k / v: operand dicts {t: bf16 CUDA tensor, off: element
+    offset, batch_stride, head_stride, row_stride, rows, batch, [rows0, norm: [(w [128] bf16, rope [n,64,2] fp32) | None] * 2]};
+    out: bf16 [batch, Sq, heads*128]."""
+    lib = load_library()
+    a = _AttnArgs()
+    for name, op in (("q", q), ("k", k), ("v", v)):
+        src = getattr(a, name)
+        t = op["t"]
+        assert t.dtype == torch.bfloat16 and t.is_cuda
+        src.ptr = t.data_ptr() + 2 * op.get("off", 0)
+        src.batch_stride, src.head_stride, src.row_stride = op["batch_stride"], op["head_stride"], op["row_stride"]
+        src.rows, src.rows0, src.batch = op["rows"], op.get("rows0", op["rows"]), op["batch"]
+        for i, nm in enumerate(op.get("norm", ())):
+            if nm is not None:
+                w, rope = nm
+                assert rope.dtype == torch.float32 and rope.shape[-2:] == (64, 2) and rope.is_contiguous() and w.dtype == torch.bfloat16
+                src.norm_w[i], src.rope[i] = w.data_ptr(), rope.data_ptr()
+    a.out, a.out_batch_stride = out.data_ptr(), out.stride(0)
+    a.batch, a.heads = out.shape[0], heads
+    a.kv_batch_map = kv_batch_map.data_ptr() if kv_batch_map is not None else None
+    a.scale = scale if scale is not None else 128 ** -0.5
+    a.norm_kind, a.eps, a.impl = norm_kind, eps, impl
+    for i in range(4):
+        a.dbg[i] = dbg[i]
+    _check(lib.foley_attention(ctypes.byref(a), stream))
+    return out

@@ -189,6 +189,38 @@ foley_status foley_gemm(const void* a, int32_t dtype, int64_t batch, int64_t row
                         int32_t mode, int32_t act, const void* bias, void* out, int64_t ldo,
                         int64_t out_batch_stride, int64_t split_stride, void* stream);
 
+/* softmax(Q K^T * scale) V for head_dim 128 (replaces F.scaled_dot_product_attention at attn_layers.py:422 and
+ * hifi_foley.py:383), with the q/k RMSNorm + RoPE of the reference's attention modules (attn_layers.py:112-148,
+ * norm_layers.py:49-51, hifi_foley.py:376-381) optionally folded into the operand load.  Element (b, h, r, d) of an
+ * operand lives at ptr + b*batch_stride + h*head_stride + r*row_stride + d (bf16, device, 16-byte aligned).  For q and
+ * k, rows [0, rows0) and [rows0, rows) form two groups (joint attention: visual tokens, then audio tokens): a group with
+ * norm_w[i] != NULL is RMS-normalised with that [128] weight and rotated with the fp32 [group rows][64][2] (cos, sin)
+ * table rope[i], indexed by the row inside the group.  out: bf16 [batch, Sq, heads*128].
+ * impl 0: tcgen05 / TMEM kernel; impl 1: the round-1 mma.sync kernel (prepared [B,H,S,128] inputs without norm only). */
+typedef struct foley_attn_src {
+    const void* ptr;
+    int64_t batch_stride, head_stride, row_stride;   /* elements */
+    int32_t rows;                     /* rows per (sample, head) */
+    int32_t rows0;                    /* rows of the first norm group (rows: one group) */
+    int32_t batch;                    /* samples behind ptr (kv operands: the number of condition sets) */
+    int32_t reserved;
+    const void* norm_w[2];
+    const float* rope[2];
+} foley_attn_src;
+typedef struct foley_attn_args {
+    foley_attn_src q, k, v;
+    void* out;
+    int64_t out_batch_stride;
+    int32_t batch, heads;
+    const int32_t* kv_batch_map;      /* device, [batch]: kv sample of query sample b; NULL = b */
+    float scale;                      /* softmax scale (1/sqrt(128)) */
+    int32_t norm_kind;                /* 0: custom RMSNorm, two roundings (triple blocks); 1: nn.RMSNorm on bf16 (single blocks) */
+    float eps;
+    int32_t impl;
+    int32_t dbg[4];                   /* [0] = 1 + chunk whose phases CTA 0 stamps with clock64 (foley_debug_times); 0 = off */
+} foley_attn_args;
+foley_status foley_attention(const foley_attn_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
