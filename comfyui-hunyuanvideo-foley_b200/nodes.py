@@ -96,6 +96,22 @@ class FoleyModel:
         kw = cfg.model_config.model_kwargs
         self.clip_len = kw.get("clip_length", 64)
         self.sync_len = kw.get("sync_length", 192)
+        self._make_engine = None      # device -> FoleyEngine with the same weights (multi-GPU replicas, parallel.py)
+        self._replicas = {}
+
+    def on_device(self, device):
+        """This model on another GPU of the process: the same weights loaded into a second engine (weights are replicated,
+        variations are sharded: SURVEY.md §8e), built on first use and cached."""
+        device = torch.device(device)
+        if device == self.engine.device:
+            return self
+        if device.index not in self._replicas:
+            if self._make_engine is None:
+                raise FoleyError("this FoleyModel cannot be replicated (no weight source kept); build it with from_state_dict / from_safetensors")
+            rep = FoleyModel(self._make_engine(device), self.empty_clip_feat, self.empty_sync_feat, self.cfg, self.dtype)
+            logger.info("Replicated the HunyuanVideoFoley weights on %s", device)
+            self._replicas[device.index] = rep
+        return self._replicas[device.index]
 
     @classmethod
     def from_state_dict(cls, state_dict, model_size=None, device=None, dtype=torch.bfloat16, quantization="none"):
@@ -104,10 +120,16 @@ class FoleyModel:
         model_size = model_size or detect_model_size(state_dict)
         cfg = load_model_config(model_size)
         engine = FoleyEngine(dict(cfg.model_config.model_kwargs), device=device, with_dac=False)
-        engine.set_fp8_weight_storage(quantization)
-        engine.load_state_dict(state_dict)
-        engine.finalize()
-        return cls(engine, state_dict["empty_clip_feat"], state_dict["empty_sync_feat"], cfg, dtype)
+        def make(dev, sd=state_dict):
+            e = FoleyEngine(dict(cfg.model_config.model_kwargs), device=dev, with_dac=False)
+            e.set_fp8_weight_storage(quantization)
+            e.load_state_dict(sd)
+            e.finalize()
+            return e
+        m = cls(make(device), state_dict["empty_clip_feat"], state_dict["empty_sync_feat"], cfg, dtype)
+        if torch.cuda.is_available() and torch.cuda.device_count() > 1:
+            m._make_engine = make          # (keeps the state dict alive: only when there is a second GPU to replicate onto)
+        return m
 
     @classmethod
     def from_safetensors(cls, path, precision="bf16", quantization="auto", device=None, cfg=None):
@@ -127,13 +149,17 @@ class FoleyModel:
         w = header.get("audio_embedder.proj.weight")
         model_size = "xl" if w is not None and int(w["shape"][0]) == 1408 else "xxl"
         cfg = cfg if cfg is not None else load_model_config(model_size)
-        engine = FoleyEngine(dict(cfg.model_config.model_kwargs), device=device, with_dac=False)
-        engine.set_fp8_weight_storage(qmode)
-        n = engine.load_safetensors(path)
-        engine.finalize()
-        logger.info("Loaded %d tensors from %s straight into the B200 engine (fp8 storage emulation: %s)", n, path, qmode)
-        return cls(engine, ck.read_tensor(path, "empty_clip_feat", header, data_start),
-                   ck.read_tensor(path, "empty_sync_feat", header, data_start), cfg, dtype)
+        def make(dev):
+            e = FoleyEngine(dict(cfg.model_config.model_kwargs), device=dev, with_dac=False)
+            e.set_fp8_weight_storage(qmode)
+            n_ = e.load_safetensors(path)
+            e.finalize()
+            logger.info("Loaded %d tensors from %s straight into the B200 engine on %s (fp8 storage emulation: %s)", n_, path, e.device, qmode)
+            return e
+        m = cls(make(device), ck.read_tensor(path, "empty_clip_feat", header, data_start),
+                ck.read_tensor(path, "empty_sync_feat", header, data_start), cfg, dtype)
+        m._make_engine = make              # replicas re-read the file
+        return m
 
     def get_empty_clip_sequence(self, bs=None, len=None):      # hifi_foley.py:620-625
         len = len if len is not None else self.clip_len
@@ -165,14 +191,33 @@ class FoleyDAC:
 
     def __init__(self, engine):
         self.engine = engine
+        self._make_engine = None
+        self._replicas = {}
 
     @classmethod
     def from_state_dict(cls, state_dict, device=None):
         # DAC-only engine instance; the DiT dimensions are irrelevant for decode
         cfg = load_model_config("xxl")
-        engine = FoleyEngine(dict(cfg.model_config.model_kwargs), device=device, with_dac=False)
-        engine.load_state_dict(state_dict, prefix="dac.")
-        return cls(engine)
+
+        def make(dev, sd=state_dict):
+            e = FoleyEngine(dict(cfg.model_config.model_kwargs), device=dev, with_dac=False)
+            e.load_state_dict(sd, prefix="dac.")
+            return e
+        d = cls(make(device))
+        if torch.cuda.is_available() and torch.cuda.device_count() > 1:
+            d._make_engine = make          # the decoder is small (~300 MB fp32): the state dict is kept for replicas
+        return d
+
+    def on_device(self, device):
+        """The decoder on another GPU of the process (multi-GPU Sampler, parallel.py)."""
+        device = torch.device(device)
+        if device == self.engine.device:
+            return self
+        if device.index not in self._replicas:
+            if self._make_engine is None:
+                raise FoleyError("this FoleyDAC cannot be replicated (no weight source kept)")
+            self._replicas[device.index] = FoleyDAC(self._make_engine(device))
+        return self._replicas[device.index]
 
     def decode(self, z):
         from . import torch_ops as ops
@@ -356,9 +401,19 @@ class HunyuanFoleySampler:
         model_dict = AttributeDict(dict(hunyuan_deps))
         model_dict["foley_model"] = hunyuan_model
         model_dict["device"] = device
-        decoded_waveform, sample_rate = denoise_process_with_generator(
-            visual_feats, text_feats, audio_len_in_s, model_dict, hunyuan_cfg, guidance_scale=cfg_scale,
-            num_inference_steps=steps, batch_size=batch_size, sampler=sampler, generator=rng)
+        # batch_size is the only parallel axis of the path (reference nodes.py:228): with more than one visible GPU the
+        # variations are sharded over them — one engine + one host thread per GPU inside this process, ONE broadcast of the
+        # condition embeddings, ONE gather of the decoded waveforms (parallel.py; FOLEY_B200_GPUS=1 keeps one GPU)
+        from . import parallel
+        devices = parallel.local_devices(batch_size, device)
+        if len(devices) > 1:
+            decoded_waveform, sample_rate = parallel.denoise_sharded(
+                visual_feats, text_feats, audio_len_in_s, model_dict, hunyuan_cfg, guidance_scale=cfg_scale,
+                num_inference_steps=steps, batch_size=batch_size, sampler=sampler, generator=rng, devices=devices)
+        else:
+            decoded_waveform, sample_rate = denoise_process_with_generator(
+                visual_feats, text_feats, audio_len_in_s, model_dict, hunyuan_cfg, guidance_scale=cfg_scale,
+                num_inference_steps=steps, batch_size=batch_size, sampler=sampler, generator=rng)
         waveform_batch = decoded_waveform.float().cpu()
         audio_output_first = {"waveform": waveform_batch[0].unsqueeze(0), "sample_rate": sample_rate}
         audio_output_batch = {"waveform": waveform_batch, "sample_rate": sample_rate}

@@ -113,3 +113,29 @@ def test_attention_fused_norm_rope(kind, Lv, L):
     err = rel_l2(out.float(), want)
     print(f"[fused kind={kind} Lv={Lv} L={L}] vs fp32 restatement: {err:.3e}")
     assert err <= TOL
+
+
+@pytest.mark.parametrize("env", [{"FOLEY_ATT_TC": "1"}, {"FOLEY_ATT_TC": "1", "FOLEY_ATT_FUSED": "1"}])
+def test_engine_forward_on_the_tcgen05_attention(env, monkeypatch):
+    """The whole DiT forward with every attention call on the tcgen05 kernel (prepared operands, and with the
+    q/k-norm + RoPE folded into its operand load: no qk_norm_rope_kernel launch) against the oracle, same tolerance as
+    the default path (tests/test_gpu_dit.py), and against the default path itself."""
+    from oracle import foley_oracle as O
+    from test_gpu_dit import _inputs, make_engine
+    eng0, c, sd = make_engine("small")
+    x, t, cond, clip, sync = _inputs(c, 2, 125, 20, 48)
+    eng0.set_conditions(clip.cuda(), sync.cuda(), cond.cuda(), L=125, batch=1)
+    base = eng0.dit_forward(x.cuda(), t).cpu()
+    n0 = eng0.launch_count()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)          # read at engine creation
+    eng, _, _ = make_engine("small", sd=sd)
+    eng.set_conditions(clip.cuda(), sync.cuda(), cond.cuda(), L=125, batch=1)
+    out = eng.dit_forward(x.cuda(), t).cpu()
+    assert eng.debug_flags()[0] == 0
+    want16 = O.dit_forward(sd, c, x, t, cond, clip, sync, policy="cuda_bf16")
+    r16, rb = rel_l2(out, want16), rel_l2(out, base)
+    print(f"\n[{env}] engine vs oracle(cuda_bf16) {r16:.3e} | vs the default attention path {rb:.3e} | launches {eng.launch_count()} vs {n0}")
+    assert r16 <= 4e-3 and rb <= 4e-3
+    if "FOLEY_ATT_FUSED" in env:
+        assert eng.launch_count() < n0       # the q/k-norm launches are gone
