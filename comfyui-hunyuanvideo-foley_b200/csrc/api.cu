@@ -49,6 +49,88 @@ extern "C" foley_status foley_gemm(const void* a, int32_t dtype, int64_t batch, 
     return FOLEY_OK;
 }
 
+// ---- row-wise kernels, one by one (unit tests)
+static const int* identity_map(int n) {   // device iota: the group maps of a stand-alone call (sample b = group b = row b)
+    static int* dev[16] = {};
+    static int cap[16] = {};
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 15;
+    if (cap[d] < n) {
+        if (dev[d]) cudaFree(dev[d]);
+        const int c = std::max(n, 256);
+        std::vector<int> h(c);
+        for (int i = 0; i < c; ++i) h[i] = i;
+        if (cudaMalloc(&dev[d], c * sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemcpy(dev[d], h.data(), c * sizeof(int), cudaMemcpyHostToDevice);
+        cap[d] = c;
+    }
+    return dev[d];
+}
+
+extern "C" foley_status foley_qk_norm_rope(const void* src, const float* partials, int32_t splits, const void* bias, int64_t src_ld,
+                                           int32_t n_parts, int32_t batch, int32_t L, int32_t heads, int32_t norm_kind, float eps,
+                                           const void* const* norm_w, const float* cos_t, const float* sin_t, void* const* dst,
+                                           int32_t S_total, int32_t seq_offset, void* stream) {
+    if ((!src && !partials) || !norm_w || !dst || n_parts < 1 || n_parts > 3 || batch < 1 || L < 1 || heads < 1)
+        return fail(FOLEY_ERR_INVALID, "foley_qk_norm_rope: bad argument");
+    QkvArgs q;
+    q.src = static_cast<const __nv_bfloat16*>(src); q.src_ld = static_cast<int>(src_ld); q.n_parts = n_parts; q.H = heads; q.L = L;
+    q.rows_total = batch * L; q.norm_kind = norm_kind; q.eps = eps; q.cos = cos_t; q.sin = sin_t;
+    if (partials) {
+        q.partials = partials; q.splits = splits; q.split_stride = static_cast<long long>(batch) * L * src_ld;
+        q.bias = static_cast<const __nv_bfloat16*>(bias);
+    }
+    for (int p = 0; p < n_parts; ++p) {
+        if (!dst[p]) return fail(FOLEY_ERR_INVALID, "foley_qk_norm_rope: null destination");
+        if (norm_w[p] && (!cos_t || !sin_t)) return fail(FOLEY_ERR_INVALID, "foley_qk_norm_rope: norm needs cos / sin tables");
+        q.part[p].dst = static_cast<__nv_bfloat16*>(dst[p]);
+        q.part[p].dst_batch_stride = static_cast<long long>(heads) * S_total * 128;
+        q.part[p].dst_head_stride = static_cast<long long>(S_total) * 128;
+        q.part[p].seq_offset = seq_offset;
+        q.part[p].norm_w = static_cast<const __nv_bfloat16*>(norm_w[p]);
+        q.part[p].src_col = p * heads * 128;
+    }
+    const long long warps = static_cast<long long>(q.rows_total) * n_parts * heads;
+    FOLEY_CUDA_OK(launch_k(qk_norm_rope_kernel, dim3(static_cast<unsigned>((warps + 3) / 4)), dim3(128), 0,
+                           static_cast<cudaStream_t>(stream), q));
+    return FOLEY_OK;
+}
+
+extern "C" foley_status foley_combine_ln_mod(const float* partials, int32_t splits, const void* bias, const void* mod,
+                                             int64_t mod_sample_stride, int64_t mod_tok_stride, int32_t gate_chunk,
+                                             int32_t shift_chunk, int32_t scale_chunk, float* x, const void* x_init, int32_t round_x,
+                                             void* h, float eps, int32_t batch, int32_t L, int32_t C, void* stream) {
+    if (!x || batch < 1 || L < 1 || C < 128 || C % 128 != 0 || C > 2048)
+        return fail(FOLEY_ERR_INVALID, "foley_combine_ln_mod: bad argument (C must be a multiple of 128 <= 2048)");
+    if ((gate_chunk >= 0 || shift_chunk >= 0) && !mod) return fail(FOLEY_ERR_INVALID, "foley_combine_ln_mod: modulation vectors missing");
+    const int* iota = identity_map(batch);
+    if (!iota) return fail(FOLEY_ERR_CUDA, "foley_combine_ln_mod: out of memory");
+    CombineArgs a;
+    a.partials = partials; a.splits = splits; a.split_stride = static_cast<long long>(batch) * L * C;
+    a.bias = static_cast<const __nv_bfloat16*>(bias);
+    ModRef m;
+    m.base = static_cast<const __nv_bfloat16*>(mod); m.sample_stride = mod_sample_stride; m.tok_stride = mod_tok_stride; m.by_trow = 0;
+    if (gate_chunk >= 0) { a.gate = m; a.gate_chunk = gate_chunk; }
+    a.x = x; a.x_init = static_cast<const __nv_bfloat16*>(x_init); a.round_x = round_x;
+    a.h = static_cast<__nv_bfloat16*>(h); a.eps = eps;
+    if (shift_chunk >= 0) { a.mod = m; a.shift_chunk = shift_chunk; a.scale_chunk = scale_chunk; }
+    a.C = C; a.rows_total = batch * L;
+    a.rm = RowMap{iota, iota, iota, L};
+    FOLEY_CUDA_OK(launch_k(combine_ln_mod_kernel, dim3(a.rows_total), dim3(C / 4), 0, static_cast<cudaStream_t>(stream), a));
+    return FOLEY_OK;
+}
+
+extern "C" foley_status foley_cfg_euler(const void* y, float* lat, void* x_next, int32_t B, int32_t n_cond, int32_t ch, int32_t L,
+                                        float guidance, const float* sigmas_dev, const int32_t* step_dev, void* stream) {
+    if (!y || !lat || !x_next || !sigmas_dev || !step_dev || B < 1 || n_cond < 1 || n_cond > 2 || ch < 1 || L < 1)
+        return fail(FOLEY_ERR_INVALID, "foley_cfg_euler: bad argument");
+    dim3 blk(32, 8), grid((L + 31) / 32, (ch + 31) / 32, B);
+    FOLEY_CUDA_OK(launch_k(cfg_euler_kernel, grid, blk, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(y),
+                           lat, static_cast<__nv_bfloat16*>(x_next), B, n_cond, ch, L, guidance, sigmas_dev, step_dev));
+    return FOLEY_OK;
+}
+
 static AttOperand to_att_operand(const foley_attn_src& s, int heads) {
     AttOperand o;
     o.ptr = static_cast<const __nv_bfloat16*>(s.ptr);
@@ -241,7 +323,8 @@ extern "C" foley_status foley_set_conditions(foley_engine* e, const void* clip, 
     if (dtype != FOLEY_DT_BF16 && dtype != FOLEY_DT_F32 && dtype != FOLEY_DT_F16)
         return fail(FOLEY_ERR_INVALID, "foley_set_conditions: dtype");
     API_GUARD_BEGIN
-    return e->impl.set_conditions(clip, sync, text, dtype, n_cond, Lv, S, T, L, batch, e->impl.pick_stream(stream));
+    foley_status s_ = e->impl.set_conditions(clip, sync, text, dtype, n_cond, Lv, S, T, L, batch, e->impl.pick_stream(stream));
+    return s_ != FOLEY_OK ? s_ : e->impl.order_after(stream);
     API_GUARD_END
 }
 
@@ -249,7 +332,8 @@ extern "C" foley_status foley_dit_forward(foley_engine* e, const float* x, const
                                           void* stream) {
     if (!e || !x || !t || !out) return fail(FOLEY_ERR_INVALID, "foley_dit_forward: null argument");
     API_GUARD_BEGIN
-    return e->impl.forward(x, t, n_t, out, e->impl.pick_stream(stream));
+    foley_status s_ = e->impl.forward(x, t, n_t, out, e->impl.pick_stream(stream));
+    return s_ != FOLEY_OK ? s_ : e->impl.order_after(stream);
     API_GUARD_END
 }
 
@@ -257,7 +341,8 @@ extern "C" foley_status foley_denoise(foley_engine* e, float* latents, const flo
                                       float guidance, foley_progress_fn progress, void* user, void* stream) {
     if (!e || !latents || !sigmas) return fail(FOLEY_ERR_INVALID, "foley_denoise: null argument");
     API_GUARD_BEGIN
-    return e->impl.denoise(latents, sigmas, n_steps, guidance, FOLEY_SOLVER_EULER, progress, user, e->impl.pick_stream(stream));
+    foley_status s_ = e->impl.denoise(latents, sigmas, n_steps, guidance, FOLEY_SOLVER_EULER, progress, user, e->impl.pick_stream(stream));
+    return s_ != FOLEY_OK ? s_ : e->impl.order_after(stream);
     API_GUARD_END
 }
 
@@ -266,7 +351,8 @@ extern "C" foley_status foley_denoise_solver(foley_engine* e, float* latents, co
                                              void* stream) {
     if (!e || !latents || !sigmas) return fail(FOLEY_ERR_INVALID, "foley_denoise_solver: null argument");
     API_GUARD_BEGIN
-    return e->impl.denoise(latents, sigmas, n_calls, guidance, solver, progress, user, e->impl.pick_stream(stream));
+    foley_status s_ = e->impl.denoise(latents, sigmas, n_calls, guidance, solver, progress, user, e->impl.pick_stream(stream));
+    return s_ != FOLEY_OK ? s_ : e->impl.order_after(stream);
     API_GUARD_END
 }
 
@@ -295,7 +381,8 @@ extern "C" foley_status foley_dac_decode(foley_engine* e, const float* z, int32_
         foley_status s = e->impl.dac_finalize();
         if (s != FOLEY_OK) return s;
     }
-    return e->impl.dac_decode(z, batch, L, wav, e->impl.pick_stream(stream));
+    foley_status s_ = e->impl.dac_decode(z, batch, L, wav, e->impl.pick_stream(stream));
+    return s_ != FOLEY_OK ? s_ : e->impl.order_after(stream);
     API_GUARD_END
 }
 

@@ -62,6 +62,7 @@ Engine::~Engine() {
     if (side_stream) cudaStreamDestroy(side_stream);
     if (mod_stream) cudaStreamDestroy(mod_stream);
     if (ev_mod) cudaEventDestroy(ev_mod);
+    if (ev_null) cudaEventDestroy(ev_null);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     free_plan();
@@ -91,6 +92,7 @@ foley_status Engine::create(const foley_config* c, int dev) {
     FOLEY_CUDA_OK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
     FOLEY_CUDA_OK(cudaStreamCreateWithFlags(&mod_stream, cudaStreamNonBlocking));
     FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_mod, cudaEventDisableTiming));
+    FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_null, cudaEventDisableTiming));
     if (const char* e = getenv("FOLEY_MOD_BRANCH")) mod_on_branch = atoi(e) != 0;
     if (const char* e = getenv("FOLEY_QKV_SPLIT")) qkv_split = atoi(e) != 0;
     if (const char* e = getenv("FOLEY_PLAN")) sscanf(e, "%lf,%lf,%lf,%lf", &plan_tkb128, &plan_tkb256, &plan_tfix, &plan_tsplit);

@@ -142,6 +142,18 @@ class Engine {
     bf16 *sc_e = nullptr, *sc_h1 = nullptr, *sc_vs = nullptr;
     int* sc_idx = nullptr;
     cudaStream_t pick_stream(void* st) { return st ? static_cast<cudaStream_t>(st) : own_stream; }
+    // A caller on the legacy default stream (torch's default) gets legacy-stream ordering: the work went to this engine's own
+    // blocking stream (the legacy stream cannot be captured), so the legacy stream is made to wait for it — otherwise the
+    // next consumer on ANOTHER blocking stream (e.g. the DAC engine's own stream decoding the latents this engine has just
+    // enqueued) would not be ordered behind it.
+    cudaEvent_t ev_null = nullptr;
+    foley_status order_after(void* caller_stream) {
+        if (caller_stream) return FOLEY_OK;
+        FOLEY_CUDA_OK(cudaSetDevice(device));
+        FOLEY_CUDA_OK(cudaEventRecord(ev_null, own_stream));
+        FOLEY_CUDA_OK(cudaStreamWaitEvent(cudaStreamLegacy, ev_null, 0));
+        return FOLEY_OK;
+    }
 
     // ---- DAC
     std::vector<DacLayer*> dac_layers;

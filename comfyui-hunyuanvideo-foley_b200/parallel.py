@@ -103,10 +103,12 @@ def denoise_sharded(visual_feats, text_feats, audio_len_in_s, model_dict, cfg, g
                     batch_size, sampler, generator, devices):
     """`sampling.denoise_process_with_generator` for a batch of variations sharded over `devices` (all in this process):
     weights replicated (FoleyModel.on_device / FoleyDAC.on_device, cached), ONE broadcast of the packed condition
-    embeddings from the primary GPU (torch.cuda.comm.broadcast: NCCL when available, peer copies over NVLink otherwise),
+    embeddings from the primary GPU (torch.nn.parallel.comm.broadcast: NCCL when available, peer copies over NVLink otherwise),
     rank r runs rows shard_range(batch_size, n, r) of the one host noise draw on its own engine from its own host thread
     (the C ABI releases the GIL), ONE gather of the decoded waveforms to the primary GPU.  No per-step exchange.
     The result equals, bit for bit, running every shard alone on one GPU with `batch_slice`."""
+    from torch.nn.parallel import comm   # single-process multi-GPU collectives (NCCL broadcast / peer-copy gather)
+
     from .config import AttributeDict
     from .sampling import denoise_process_with_generator, prepare_latents_with_generator
     devices = [torch.device(d) for d in devices]
@@ -117,7 +119,7 @@ def denoise_sharded(visual_feats, text_feats, audio_len_in_s, model_dict, cfg, g
     feats = {"siglip2_feat": visual_feats["siglip2_feat"][:1], "syncformer_feat": visual_feats["syncformer_feat"][:1],
              "text_feat": text_feats["text_feat"][:1], "uncond_text_feat": text_feats["uncond_text_feat"][:1]}
     flat, shapes = pack_conditions({k: v.to(primary) for k, v in feats.items()}, model.dtype)
-    copies = torch.cuda.comm.broadcast(flat, [d.index for d in devices])
+    copies = comm.broadcast(flat, [d.index for d in devices])
     state = generator.get_state() if generator is not None else None
     results, errors = [None] * n, [None] * n
 
@@ -156,5 +158,5 @@ def denoise_sharded(visual_feats, text_feats, audio_len_in_s, model_dict, cfg, g
         kw = cfg.model_config.model_kwargs
         prepare_latents_with_generator(None, batch_size, kw.audio_vae_latent_dim, int(audio_len_in_s * kw.audio_frame_rate),
                                        model.dtype, "cpu", generator)
-    full = torch.cuda.comm.gather([w for w, _ in results], dim=0, destination=primary.index)
+    full = comm.gather([w for w, _ in results], dim=0, destination=primary.index)
     return full, results[0][1]

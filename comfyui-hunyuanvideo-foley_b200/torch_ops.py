@@ -10,6 +10,7 @@ north-star: "through a thin C-ABI extension surfaced as a torch op"), so the Sam
 `h` is an integer handle from `register_engine(FoleyEngine)`.  Only the CUDA dispatch key has a kernel: calling an
 op with CPU tensors raises (there is no CPU / eager path), the Meta key gives shapes for tracing tools.
 """
+import threading
 import weakref
 
 import torch
@@ -21,17 +22,19 @@ SOLVER_IDS = {"euler": 0, "heun-2": 1, "midpoint-2": 2, "kutta-4": 3}
 
 _engines = weakref.WeakValueDictionary()
 _next_handle = [1]
+_handle_lock = threading.Lock()   # the multi-GPU Sampler registers one engine per host thread (parallel.denoise_sharded)
 
 
 def register_engine(engine):
-    """Returns the integer handle the ops take for `engine` (idempotent)."""
-    h = getattr(engine, "_op_handle", None)
-    if h is None or _engines.get(h) is not engine:
-        h = _next_handle[0]
-        _next_handle[0] += 1
-        engine._op_handle = h
-        _engines[h] = engine
-    return h
+    """Returns the integer handle the ops take for `engine` (idempotent, thread-safe)."""
+    with _handle_lock:
+        h = getattr(engine, "_op_handle", None)
+        if h is None or _engines.get(h) is not engine:
+            h = _next_handle[0]
+            _next_handle[0] += 1
+            engine._op_handle = h
+            _engines[h] = engine
+        return h
 
 
 def _engine(handle):

@@ -189,6 +189,32 @@ foley_status foley_gemm(const void* a, int32_t dtype, int64_t batch, int64_t row
                         int32_t mode, int32_t act, const void* bias, void* out, int64_t ldo,
                         int64_t out_batch_stride, int64_t split_stride, void* stream);
 
+/* ---- the row-wise kernels of the step, exported one by one for unit tests (tests/test_gpu_rowwise.py) ---- */
+/* q/k RMSNorm + RoPE + scatter to the attention layout (csrc/rowwise.cuh qk_norm_rope_kernel; reference
+ * attn_layers.py:112-148, norm_layers.py:49-51, hifi_foley.py:376-381).  Source rows: bf16 [batch*L, src_ld] with the
+ * parts laid out (part, head, 128), or — partials != NULL — the fp32 K-split partials [splits, batch*L, src_ld] of the
+ * projection GEMM plus its bf16 bias.  Part p of row (b, l) lands at dst[p][b, head, seq_offset + l, :] of a
+ * [batch, heads, S_total, 128] bf16 tensor; norm_w[p] == NULL copies the part (v).  cos / sin: fp32 [L, 128]. */
+foley_status foley_qk_norm_rope(const void* src, const float* partials, int32_t splits, const void* bias, int64_t src_ld,
+                                int32_t n_parts, int32_t batch, int32_t L, int32_t heads, int32_t norm_kind, float eps,
+                                const void* const* norm_w, const float* cos_t, const float* sin_t, void* const* dst,
+                                int32_t S_total, int32_t seq_offset, void* stream);
+/* K-split reduce + bias + gate + residual + LayerNorm + modulate (combine_ln_mod_kernel; reference hifi_foley.py:216-331,
+ * 364-390 and modulate_layers.py): for every row (b, l) of [batch*L, C]
+ *   y = bf16(sum_s partials[s] + bias); y = bf16(y * gate) if gate_chunk >= 0; x += y (x rounded to bf16 if round_x);
+ *   h = bf16(LayerNorm(x) * bf16(1 + scale) + shift)      (plain LayerNorm when shift_chunk < 0)
+ * Modulation vectors (bf16): chunk k of row (b, l) at mod + b*mod_sample_stride + l*mod_tok_stride + k*C.
+ * partials == NULL skips the residual update; x_init (bf16 [batch*L, C]) replaces the incoming x; h == NULL skips the norm. */
+foley_status foley_combine_ln_mod(const float* partials, int32_t splits, const void* bias, const void* mod,
+                                  int64_t mod_sample_stride, int64_t mod_tok_stride, int32_t gate_chunk, int32_t shift_chunk,
+                                  int32_t scale_chunk, float* x, const void* x_init, int32_t round_x, void* h, float eps,
+                                  int32_t batch, int32_t L, int32_t C, void* stream);
+/* bf16 CFG combine + fp32 Euler update + next bf16 model input (cfg_euler_kernel; reference utils.py:241-243,
+ * scheduling_flow_match_discrete.py:262-297).  y: bf16 [n_cond*B, L, ch] (unconditional rows first); lat: fp32 [B, ch, L]
+ * in/out; x_next: bf16 [n_cond*B, L, ch]; the step size is sigmas[step+1] - sigmas[step] (device arrays). */
+foley_status foley_cfg_euler(const void* y, float* lat, void* x_next, int32_t B, int32_t n_cond, int32_t ch, int32_t L,
+                             float guidance, const float* sigmas_dev, const int32_t* step_dev, void* stream);
+
 /* softmax(Q K^T * scale) V for head_dim 128 (replaces F.scaled_dot_product_attention at attn_layers.py:422 and
  * hifi_foley.py:383), with the q/k RMSNorm + RoPE of the reference's attention modules (attn_layers.py:112-148,
  * norm_layers.py:49-51, hifi_foley.py:376-381) optionally folded into the operand load.  Element (b, h, r, d) of an

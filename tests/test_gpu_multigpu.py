@@ -72,5 +72,27 @@ def test_sampler_shards_variations_over_two_gpus(monkeypatch):
     monkeypatch.setenv("FOLEY_B200_GPUS", "1")
     wav1 = run()
     err = rel_l2(wav2, wav1)
-    print(f"\\n2-GPU sharded vs 1-GPU batch of {B}: waveform rel-L2 {err:.3e}")
+    print(f"2-GPU sharded vs 1-GPU batch of {B}: waveform rel-L2 {err:.3e}")
     assert err <= 3e-2
+
+
+def test_default_stream_denoise_then_decode_is_ordered():
+    """Regression (round 2): called on the legacy default stream without a progress callback, the DiT engine enqueues the
+    whole loop on ITS blocking stream and returns; the DAC engine then decodes on ANOTHER blocking stream.  The C ABI now
+    makes the legacy stream wait for the engine's work, so the decode is ordered behind the denoise: repeated calls give
+    the same waveform (before the fix only the first call did, thanks to the cudaMalloc of the decoder's buffers)."""
+    torch.cuda.set_device(0)
+    nodes, cfgmod, model, dac, deps, text, cfg = _objects()
+    sampling = load_pkg("sampling")
+    duration = 2.0
+    clip_len, sync_len = nodes.t2a_feature_lengths(duration)
+    visual = {"siglip2_feat": model.get_empty_clip_sequence(bs=1, len=clip_len).to("cpu", torch.bfloat16),
+              "syncformer_feat": model.get_empty_sync_sequence(bs=1, len=sync_len).to("cpu", torch.bfloat16)}
+    md = cfgmod.AttributeDict(dict(deps))
+    md["foley_model"], md["device"] = model, torch.device("cuda", 0)
+    outs = []
+    for _ in range(3):
+        gen = torch.Generator(device="cpu").manual_seed(7)
+        w, _ = sampling.denoise_process_with_generator(visual, text, duration, md, cfg, 4.5, 10, 2, "euler", generator=gen)
+        outs.append(w.float().cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
