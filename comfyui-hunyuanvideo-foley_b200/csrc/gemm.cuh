@@ -197,6 +197,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (tprobe && threadIdx.x == 0) g_foley_times[1] = clock64();
 
+    // epilogue geometry (also needed by warp 0, which issues the TMA stores of the staged epilogues)
+    constexpr int NG = Cfg::EPI_GROUPS;          // column-chunk sets: chunk c0 = half*32 + it*32*NG belongs to set `half`
+    constexpr int EPI_THREADS = 32 * Cfg::EPI_WARPS;
+    constexpr int NIT = (BN + 32 * NG - 1) / (32 * NG);
+    static_assert(NIT <= 8, "one named barrier (ids 2..9) per column group");
+
     if (g.dbg_stop == 1) {
         // setup / teardown only
     } else if (warp == 0) {
@@ -231,6 +237,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             }
         }
 #endif
+        // ---- after the mainloop this warp issues the TMA stores of the staged (bf16 / fp32) epilogues: the epilogue warps
+        // arrive on one named barrier per column group as soon as they have written it to the staging tile and move on
+        __syncwarp();
+        if (g.epi.mode != EPI_DAC && g.epi.mode != EPI_SWIGLU) {
+            const int bpc = g.epi.mode == EPI_F32 ? 4 : 2;      // output bytes per accumulator column
+            const int esz = bpc;
+            const bool live_w = (g.dbg_stop & 7) == 0 && num_kb > 0;
+            int boxes_issued = 0;
+            for (int it = 0; it < NIT; ++it) {
+                asm volatile("bar.sync %0, %1;" ::"r"(2 + it), "n"(EPI_THREADS + 32) : "memory");
+                if (lane == 0 && live_w) {
+                    const int cols_done = (it + 1) * 32 * NG < BN ? (it + 1) * 32 * NG : BN;
+                    const int boxes_done = (cols_done * bpc) >> 7;
+                    for (; boxes_issued < boxes_done; ++boxes_issued) {
+                        const int col_elem = (n0 * bpc + boxes_issued * 128) / esz;
+                        if (col_elem < g.n) tma_store_4d(&tm_c, smem + boxes_issued * 16384, col_elem, m0, batch, split);
+                    }
+                    tma_store_commit();
+                }
+            }
+            if (lane == 0) tma_store_wait_read();               // the staging memory must outlive the reads
+        }
     } else if (warp == Cfg::A_WARP) {
         // ------------------------------------------------------------- TMA producer: activation tiles
         if (lane == 0 && FOLEY_GEMM_TWO_PRODUCERS) {
@@ -311,9 +339,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // ------------------------------------------------------------- epilogue warps (2..9)
         // Two warps per TMEM lane quarter; each takes every other 32-column chunk.  Per-column parameters (bias,
         // snake alpha and 1/alpha) are staged in shared memory while the mainloop runs.
-        constexpr int NG = Cfg::EPI_GROUPS;  // column-chunk sets: chunk c0 = half*32 + it*32*NG belongs to set `half`
-        constexpr int EPI_THREADS = 32 * Cfg::EPI_WARPS;
-        constexpr int NIT = (BN + 32 * NG - 1) / (32 * NG);
         const int q = warp & 3;              // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;    // which interleaved set of column chunks
         const int r = m0 + q * 32 + lane;    // output row within the sample
@@ -348,90 +373,90 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                                   static_cast<long long>(r) * e.ldo;
         // SwiGLU tiles write only 32 bytes per row and chunk: their direct stores were never the bottleneck, and the
         // staged path costs them ~0.7 us of barriers (measured), so they keep storing from registers.
-        if (e.mode != EPI_DAC && (FOLEY_SWIGLU_STAGED ? !(BN == 64 && e.mode == EPI_SWIGLU) : e.mode != EPI_SWIGLU)) {
-            // ---- DiT epilogues: the tile goes through shared memory (the idle operand ring) and leaves as TMA stores.
-            // A thread owns one accumulator ROW, so direct stores made every warp instruction touch 32 different
-            // lines (measured 2.5-6.5 us per tile, LSU-transaction bound); staged, the tile is written to global as
-            // whole 128-byte lines by the copy engine while the warps move on.  Staging layout = TMA boxes of
-            // 128 rows x 128 B with the 128-byte swizzle (16-byte piece index ^ (row & 7)): conflict-free for one
-            // row per thread.  bpc = output bytes per accumulator column: 4 (fp32 partials), 2 (bf16), 1 (SwiGLU pairs).
-            const int bpc = e.mode == EPI_F32 ? 4 : (e.mode == EPI_BF16 ? 2 : 1);
-            const int esz = e.mode == EPI_F32 ? 4 : 2;
-            const int n_out = e.mode == EPI_SWIGLU ? g.n >> 1 : g.n;
+        if (e.mode != EPI_DAC && e.mode != EPI_SWIGLU) {
+            // ---- DiT epilogues (bf16 + bias + activation, fp32 K-split partials): the tile goes through shared memory (the
+            // idle operand ring) and leaves as TMA stores.  A thread owns one accumulator ROW, so direct stores made every
+            // warp instruction touch 32 different lines (measured 2.5-6.5 us per tile, LSU-transaction bound); staged, the
+            // tile is written to global as whole 128-byte lines by the copy engine.  Staging layout = TMA boxes of
+            // 128 rows x 128 B with the 128-byte swizzle (16-byte piece index ^ (row & 7)): conflict-free for one row
+            // per thread.  Round 2 (tools/gemm_micro.py --dbg 8 showed 3.9 us per bf16 tile, 2.9 us per fp32 tile):
+            //   * the activation switch is hoisted out of the element loop (it cost ~60 cycles per element),
+            //   * the tcgen05.ld of the next chunk is in flight while this one is converted,
+            //   * the epilogue warps only ARRIVE on a per-chunk named barrier; warp 0 (idle after the mainloop) waits on it
+            //     and issues the TMA stores, so no epilogue warp stalls behind the store issue (~0.35 us per chunk).
+            const int bpc = e.mode == EPI_F32 ? 4 : 2;
             const uint32_t r_local = static_cast<uint32_t>(q * 32 + lane);
             const uint32_t stage_base = smem_u32(smem);
+            const uint32_t epi_s = smem_u32(epi_f);
             const bool live = acc_ok && (g.dbg_stop & 7) == 0 && num_kb > 0;
-            int boxes_issued = 0;
+            const uint32_t sw = r_local & 7u;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32;
+            auto chunk_ok = [&](int it) {
+                const int c0 = half * 32 + it * 32 * NG;
+                return live && it < NIT && c0 < BN && n0 + c0 < g.n;
+            };
             // One accumulator chunk (32 columns of this thread's row) -> fused math -> swizzled staging row.
-            auto emit = [&](const uint32_t (&v)[32], int c0) {
-                const float* pb = epi_f + c0;
+            auto emit = [&](uint32_t (&v)[32], int c0) {
                 const uint32_t byte_off = static_cast<uint32_t>(c0 * bpc);
                 const uint32_t row_addr = stage_base + (byte_off >> 7) * 16384u + r_local * 128u;
                 const uint32_t piece0 = (byte_off & 127u) >> 4;
-                const uint32_t sw = r_local & 7u;
                 if (e.mode == EPI_F32) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         st_shared_v4(row_addr + (((piece0 + j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                } else if (e.mode == EPI_BF16) {
-                    uint32_t packed[16];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float a0 = __uint_as_float(v[j]) + pb[j], a1 = __uint_as_float(v[j + 1]) + pb[j + 1];
-                        if (e.act == ACT_SILU) {
-                            a0 = bf16_round(a0); a1 = bf16_round(a1);
-                            a0 = __fdividef(a0, 1.0f + __expf(-a0));
-                            a1 = __fdividef(a1, 1.0f + __expf(-a1));
-                        } else if (e.act != ACT_NONE) {
-                            a0 = apply_act(bf16_round(a0), e.act);
-                            a1 = apply_act(bf16_round(a1), e.act);
-                        }
-                        packed[j >> 1] = pack_bf16x2(a0, a1);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        st_shared_v4(row_addr + (((piece0 + j) ^ sw) << 4), packed[4 * j], packed[4 * j + 1],
-                                     packed[4 * j + 2], packed[4 * j + 3]);
-                } else {   // EPI_SWIGLU
-                    uint32_t packed[8];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float g0 = bf16_round(__uint_as_float(v[j])), u0 = bf16_round(__uint_as_float(v[j + 1]));
-                        const float g1 = bf16_round(__uint_as_float(v[j + 2])), u1 = bf16_round(__uint_as_float(v[j + 3]));
-                        const float s0 = bf16_round(__fdividef(g0, 1.0f + __expf(-g0))) * u0;
-                        const float s1 = bf16_round(__fdividef(g1, 1.0f + __expf(-g1))) * u1;
-                        packed[j >> 2] = pack_bf16x2(s0, s1);
-                    }
-                    st_shared_v4(row_addr + (((piece0 + 0) ^ sw) << 4), packed[0], packed[1], packed[2], packed[3]);
-                    st_shared_v4(row_addr + (((piece0 + 1) ^ sw) << 4), packed[4], packed[5], packed[6], packed[7]);
+                    return;
                 }
+                float a[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {     // bias of these 32 columns (staged as fp32)
+                    uint32_t b0, b1, b2, b3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(epi_s + (c0 + 4 * j) * 4));
+                    a[4 * j] = __uint_as_float(v[4 * j]) + __uint_as_float(b0);
+                    a[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + __uint_as_float(b1);
+                    a[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + __uint_as_float(b2);
+                    a[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + __uint_as_float(b3);
+                }
+                if (e.act == ACT_SILU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { const float x = bf16_round(a[j]); a[j] = __fdividef(x, 1.0f + __expf(-x)); }
+                } else if (e.act == ACT_GELU_TANH) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) a[j] = gelu_tanh_f(bf16_round(a[j]));
+                } else if (e.act != ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) a[j] = apply_act(bf16_round(a[j]), e.act);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    st_shared_v4(row_addr + (((piece0 + j) ^ sw) << 4), pack_bf16x2(a[8 * j], a[8 * j + 1]), pack_bf16x2(a[8 * j + 2], a[8 * j + 3]),
+                                 pack_bf16x2(a[8 * j + 4], a[8 * j + 5]), pack_bf16x2(a[8 * j + 6], a[8 * j + 7]));
             };
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32;
-#pragma unroll 1   // (fully unrolled, the three fused epilogues x four chunks ran 40 % slower: measured)
-            for (int it = 0; it < NIT; ++it) {
-                const int c0 = half * 32 + it * 32 * NG;
-                if (live && c0 < BN && n0 + c0 < g.n) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(t_row + it * 32 * NG, v);
-                    tmem_ld_wait();
-                    emit(v, c0);
+            // registers written by an in-flight tcgen05.ld must not be touched before tcgen05.wait::ld: an empty asm with
+            // "+r" operands pins every later use behind it
+            auto pin = [](uint32_t (&v)[32]) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) asm volatile("" : "+r"(v[j]));
+            };
+            auto step = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int it) {
+                tmem_ld_wait();
+                if (chunk_ok(it + 1)) tmem_ld_32x32(t_row + (it + 1) * 32 * NG, nxt);
+                if (chunk_ok(it)) {
+                    pin(cur);
+                    if (tprobe && threadIdx.x == 64 && it == 0) g_foley_times[9] = clock64();
+                    emit(cur, half * 32 + it * 32 * NG);
+                    if (tprobe && threadIdx.x == 64 && it == 0) g_foley_times[10] = clock64();
                 }
-                {   // every column group leaves as soon as all epilogue warps have written it
-                    fence_proxy_async();                          // generic-proxy smem writes -> visible to the TMA store
-                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-                    if (threadIdx.x == 64 && live) {
-                        const int cols_done = (it + 1) * 32 * NG < BN ? (it + 1) * 32 * NG : BN;
-                        const int boxes_done = (cols_done * bpc) >> 7;
-                        for (; boxes_issued < boxes_done; ++boxes_issued) {
-                            const int col_elem = (n0 * bpc + boxes_issued * 128) / esz;
-                            if (col_elem < n_out)
-                                tma_store_4d(&tm_c, smem + boxes_issued * 16384, col_elem, m0, batch, split);
-                        }
-                        tma_store_commit();
-                    }
-                }
+                fence_proxy_async();                          // generic-proxy smem writes -> visible to the TMA store
+                asm volatile("bar.arrive %0, %1;" ::"r"(2 + it), "n"(EPI_THREADS + 32) : "memory");   // warp 0 stores this column group
+            };
+            uint32_t va[32], vb[32];
+            if (chunk_ok(0)) tmem_ld_32x32(t_row, va);
+#pragma unroll 1
+            for (int it = 0; it < NIT; it += 2) {
+                step(va, vb, it);
+                if (it + 1 < NIT) step(vb, va, it + 1);
             }
-            if (threadIdx.x == 64) tma_store_wait_read();         // the staging memory must outlive the reads
+            if (tprobe && threadIdx.x == 64) g_foley_times[13] = clock64();
         } else
 #pragma unroll 1
         for (int c0 = half * 32; c0 < BN && acc_ok && (g.dbg_stop & 7) == 0; c0 += 32 * NG) {
@@ -486,10 +511,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                             reinterpret_cast<float4*>(out)[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
                     }
                     if (out2) {
+                        if (e.act == ACT_TANH) {          // (the switch outside the element loop: see the staged epilogue)
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (e.act == ACT_TANH) y[j] = tanhf(y[j]);
-                            else if (snake) { const float sn = __sinf(pb[256 + j] * y[j]); y[j] = fmaf(pb[512 + j] * sn, sn, y[j]); }
+                            for (int j = 0; j < 32; ++j) y[j] = tanhf(y[j]);
+                        } else if (snake) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { const float sn = __sinf(pb[256 + j] * y[j]); y[j] = fmaf(pb[512 + j] * sn, sn, y[j]); }
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j)

@@ -197,24 +197,36 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                         } else {
                             const uint32_t row_addr = stage_base + static_cast<uint32_t>(box0) * 16384u + r_local * 128u;
                             const uint32_t piece0 = static_cast<uint32_t>(half) * 4u;
+                            // (the activation switch sits OUTSIDE the element loop: inside, it cost ~60 cycles per element;
+                            //  the bias of the 32 columns comes as four 16-byte loads)
+                            float a[32];
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) a[jj] = __uint_as_float(v[jj]);
+                            if (bias) {
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
+                                    const uint4 bw = __ldg(reinterpret_cast<const uint4*>(bias + n0 + c0) + jj);
+                                    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&bw);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        a[8 * jj + 2 * k] += __low2float(b2[k]);
+                                        a[8 * jj + 2 * k + 1] += __high2float(b2[k]);
+                                    }
+                                }
+                            }
+                            if (e.act == ACT_SILU) {
+#pragma unroll
+                                for (int jj = 0; jj < 32; ++jj) { const float x = bf16_round(a[jj]); a[jj] = __fdividef(x, 1.0f + __expf(-x)); }
+                            } else if (e.act == ACT_GELU_TANH) {
+#pragma unroll
+                                for (int jj = 0; jj < 32; ++jj) a[jj] = gelu_tanh_f(bf16_round(a[jj]));
+                            } else if (e.act != ACT_NONE) {
+#pragma unroll
+                                for (int jj = 0; jj < 32; ++jj) a[jj] = apply_act(bf16_round(a[jj]), e.act);
+                            }
                             uint32_t packed[16];
 #pragma unroll
-                            for (int jj = 0; jj < 32; jj += 2) {
-                                float a0 = __uint_as_float(v[jj]), a1 = __uint_as_float(v[jj + 1]);
-                                if (bias) {
-                                    a0 += __bfloat162float(__ldg(bias + n0 + c0 + jj));
-                                    a1 += __bfloat162float(__ldg(bias + n0 + c0 + jj + 1));
-                                }
-                                if (e.act == ACT_SILU) {
-                                    a0 = bf16_round(a0); a1 = bf16_round(a1);
-                                    a0 = __fdividef(a0, 1.0f + __expf(-a0));
-                                    a1 = __fdividef(a1, 1.0f + __expf(-a1));
-                                } else if (e.act != ACT_NONE) {
-                                    a0 = apply_act(bf16_round(a0), e.act);
-                                    a1 = apply_act(bf16_round(a1), e.act);
-                                }
-                                packed[jj >> 1] = pack_bf16x2(a0, a1);
-                            }
+                            for (int jj = 0; jj < 16; ++jj) packed[jj] = pack_bf16x2(a[2 * jj], a[2 * jj + 1]);
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj)
                                 st_shared_v4(row_addr + (((piece0 + jj) ^ sw) << 4), packed[4 * jj], packed[4 * jj + 1],

@@ -14,7 +14,9 @@ from conftest import load_pkg, rel_l2  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=200)
+ap.add_argument("--only", default="", help="run one case only: joint5 | single5 | cross5 | joint30 | single30 (ncu target)")
 ap.add_argument("--probe", action="store_true", help="clock64 timeline of CTA 0 (tcgen05 kernel)")
+ap.add_argument("--fused", action="store_true", help="also time the operand load with the q/k-norm + RoPE folded in")
 ap.add_argument("--variants", action="store_true", help="try the alternative MN-major descriptor stride assignments")
 a = ap.parse_args()
 E = load_pkg("engine")
@@ -144,16 +146,21 @@ def run_fused(name, kind, Lv, L, B=2, H=11, normed=True):
               ", ".join(f"{n} {(t[i + 1] - t[0]) / ghz:.0f}" for i, n in enumerate(names)))
 
 
-run_fused("single 5s", 1, 0, 250)
-run_fused("single 5s", 1, 0, 250, normed=False)
-run_fused("joint 5s", 0, 40, 250)
-run_fused("joint 5s", 0, 40, 250, normed=False)
+CASES = {"joint5": ("joint 5s", 2, 11, 290, 290, None), "single5": ("single 5s", 2, 11, 250, 250, None),
+         "cross5": ("cross 5s (77 text)", 2, 11, 290, 77, 2), "short": ("short", 1, 2, 40, 16, None),
+         "joint30": ("joint 30s xxl", 2, 12, 1740, 1740, None), "single30": ("single 30s xxl", 2, 12, 1500, 1500, None)}
+if a.only:
+    n_, B_, H_, Sq_, Sk_, kvB_ = CASES[a.only]
+    run(n_, B_, H_, Sq_, Sk_, kvB=kvB_, time_it=False)
+    sys.exit(0)
+if a.fused:
+    run_fused("single 5s", 1, 0, 250)
+    run_fused("single 5s", 1, 0, 250, normed=False)
+    run_fused("joint 5s", 0, 40, 250)
+    run_fused("joint 5s", 0, 40, 250, normed=False)
 if a.variants:
     for pat in ("v_ones", "v_keyidx"):
         run("joint 5s", 2, 11, 290, 290, time_it=False, pattern=pat)
-run("joint 5s", 2, 11, 290, 290)
-run("single 5s", 2, 11, 250, 250)
-run("cross 5s (77 text)", 2, 11, 290, 77, kvB=2)
-run("short", 1, 2, 40, 16)
-run("joint 30s xxl", 2, 12, 1740, 1740)
-run("single 30s xxl", 2, 12, 1500, 1500)
+for key in ("joint5", "single5", "cross5", "short", "joint30", "single30"):
+    n_, B_, H_, Sq_, Sk_, kvB_ = CASES[key]
+    run(n_, B_, H_, Sq_, Sk_, kvB=kvB_)

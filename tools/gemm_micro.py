@@ -87,6 +87,9 @@ def run(name, bn, pair=None, dbg=None):
         print(f"      CTA0 timeline: {wall_ns} ns wall, {cyc} cycles ({ghz:.2f} GHz); cumulative ns:")
         for nm, m in zip(names, marks):
             print(f"        {nm:28s} {(m - t[0]) / ghz:8.0f}")
+        if t[9]:
+            print("      epilogue, first chunk (ns after 'accumulator complete'): " +
+                  ", ".join(f"{nm} {(t[i] - t[5]) / ghz:.0f}" for nm, i in (("tcgen05.ld done", 9), ("math + st.shared", 10), ("all chunks done", 13))))
 
 
 if a.sweep:
