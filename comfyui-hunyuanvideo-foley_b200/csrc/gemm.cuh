@@ -23,9 +23,10 @@
 #define FOLEY_PAIR_DIRECT 1   // CTA-pair tiles: both CTAs' TMA loads complete on the LEADER's full barrier (cta_group::2 TMA form; the
                               // leader expects the pair's bytes) instead of the peer forwarding "stage landed" with a remote arrive
 #endif
-#ifndef FOLEY_SWIGLU_STAGED
-#define FOLEY_SWIGLU_STAGED 0     // 1: SwiGLU tiles also leave through the staging buffer (measured 0.8 us slower per tile)
-#endif
+// (SwiGLU tiles keep storing 32 bytes per row and chunk straight from registers: sending them through the staging tile +
+//  TMA stores measured slower both in round 1 (+0.8 us) and with round 2's arrive-only barriers (w1|w3 29.8 vs 29.0 us), and
+//  so did keeping the next chunk's tcgen05.ld in flight (29.2 us, 168 registers): that epilogue is bound by its math — two
+//  MUFU ops and three bf16 roundings per output — not by its stores.)
 #ifndef FOLEY_EPI_WARPS_BF16
 #define FOLEY_EPI_WARPS_BF16 8    // 16 measured: fc1 (GELU) 14.5 -> 13.7 us, but w2 / w1|w3 0.3 us slower; step 4.14 -> 4.17 ms
 #endif
