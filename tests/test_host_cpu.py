@@ -221,13 +221,19 @@ def test_world_size_2_gloo_broadcast_shard_gather(tmp_path):
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` prints one JSON line with the contract keys (tiny model keeps it fast)."""
+    """`bench.py --impl reference` prints one JSON line with the contract keys (tiny model keeps it fast): the staged
+    reference's own modules when baseline/_ref (or /root/reference) is present — complete Euler steps + a full decode,
+    extrapolation declared — else the oracle port."""
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "tiny",
                           "--steps", "1", "--warmup", "0", "--duration", "1"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "audio_seconds_per_sec" and line["higher_is_better"] is True
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1
+    if cb["kind"] == "reference":
+        assert cb["extrapolated"] is True and cb["euler_steps_timed"] >= 1 and cb["t_dac_decode_s"] > 0
+        assert abs(cb["extrapolation_factor"] - 50 / cb["euler_steps_timed"]) < 1e-9 and line["extrapolated"] is True
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["value"] > 0 and "workload" in line["config"]
 
