@@ -42,6 +42,7 @@ extern "C" foley_status foley_gemm(const void* a, int32_t dtype, int64_t batch, 
     L.splits = splits; L.bn = bn & 0xFFFF;
     L.dbg_stop = (bn >> 16) & 0xF;  // bring-up aid: upper bits of bn select a partial pipeline
     L.pair = ((bn >> 20) & 3) - 1;  // 0: default policy, 1: single-CTA tiles, 2: CTA-pair (cta_group::2) tiles
+    L.cluster_m = ((bn >> 22) & 7) ? ((bn >> 22) & 7) : -1;   // 0: default policy, else weight-tile multicast over 1 / 2 / 4 m-tiles
     L.epi.mode = mode; L.epi.act = act; L.epi.bias = bias; L.epi.out = out; L.epi.ldo = ldo;
     L.epi.out_batch_stride = out_batch_stride; L.epi.split_stride = split_stride;
     std::string err;

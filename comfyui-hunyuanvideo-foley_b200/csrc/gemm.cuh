@@ -69,6 +69,8 @@ struct GemmArgs {
                      // pass re-used), 8 = full kernel + clock64 stamps of CTA 0 (foley_debug_times)
     int prefetch_b;  // L2 prefetch distance of the weight operand in k-blocks (0 = off)
     int pf_mod;      // CTAs with blockIdx.x % pf_mod == 0 issue the prefetch (m-tiles sharing a weight column)
+    int cluster_m;   // > 1: the cluster_m CTAs of a (cluster_m,1,1) cluster (consecutive m-tiles, same weight tile) each load
+                     // 1/cluster_m of the B tile and MULTICAST it to all of them (one L2 read instead of cluster_m)
     GemmEpi epi;
 };
 
@@ -146,6 +148,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     // Each CTA's loads complete on its OWN full barrier (two arrivals per phase: the weight producer's and the
     // activation producer's expect_tx); in pair mode the peer forwards "stage landed" to the leader with one remote
     // arrive per stage (remote complete_tx from TMA, the cta_group::2 TMA form, measured slower here).
+    // weight-tile multicast across the m-tiles of a cluster (single-CTA tiles only)
+    const uint32_t cm = kPair ? 1u : static_cast<uint32_t>(g.cluster_m > 1 ? g.cluster_m : 1);
+    const uint32_t crank = cm > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = static_cast<uint16_t>((1u << cm) - 1u);
     constexpr bool kDirect = kPair && FOLEY_PAIR_DIRECT && FOLEY_GEMM_TWO_PRODUCERS;
     const uint32_t lead_full = kDirect ? mapa_u32(smem_u32(full_bar), 0) : 0;   // the leader's full barriers (shared::cluster)
     auto load_b = [&](int s, int kb) {
@@ -153,6 +159,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::B_BYTES);   // both halves of the B tile land on this barrier
             tma_load_3d_pair(smem_b + s * Cfg::B_BYTES, &tm_b, lead_full + s * 8, kb * Cfg::BK,
                              n0 + static_cast<int>(pair_rank) * Cfg::B_ROWS, 0);
+        } else if (cm > 1) {
+            // this CTA's slice of the B tile goes to every CTA of the cluster; its own barrier collects all cm slices
+            const uint32_t slice_rows = static_cast<uint32_t>(BN) / cm;
+            mbar_expect_tx(&full_bar[s], Cfg::B_BYTES);
+            tma_load_3d_mc(smem_b + s * Cfg::B_BYTES + crank * slice_rows * Cfg::BK_BYTES, &tm_b, &full_bar[s], kb * Cfg::BK,
+                           n0 + static_cast<int>(crank * slice_rows), 0, cmask);
         } else {
             mbar_expect_tx(&full_bar[s], Cfg::B_BYTES);
             tma_load_3d(smem_b + s * Cfg::B_BYTES, &tm_b, &full_bar[s], kb * Cfg::BK,
@@ -170,7 +182,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     };
     const int pre = g.dbg_stop == 1 ? 0 : (num_kb < Cfg::STAGES ? num_kb : Cfg::STAGES);
     // direct pair mode: the peer's loads signal the LEADER's barriers, which exist only after the cluster sync below
-    const int pre_early = (kDirect && !leader) ? 0 : pre;
+    const int pre_early = ((kDirect && !leader) || cm > 1) ? 0 : pre;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
@@ -178,7 +190,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         tma_prefetch_desc(&tm_c);
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full_bar[s], 2);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], cm);   // multicast: a stage is refilled (in every CTA) once all cm CTAs have consumed it
             mbar_init(&peer_ready[s], 1);
         }
         mbar_init(tmem_full_bar, 1);
@@ -193,7 +205,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if constexpr (kPair) cluster_sync_all();   // the peer's barriers must exist before anything is signalled to them
+    if (kPair || cm > 1) cluster_sync_all();   // the peers' barriers must exist before anything is signalled to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (tprobe && threadIdx.x == 0) g_foley_times[1] = clock64();
@@ -304,6 +316,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 if (tprobe && i == 0) g_foley_times[3] = clock64();
                 if (g.dbg_stop == 2) {
                     if constexpr (kPair) { mbar_arrive(&empty_bar[s]); mbar_arrive_cluster(mapa_u32(smem_u32(&empty_bar[s]), 1)); }
+                    else if (cm > 1) { for (uint32_t rk = 0; rk < cm; ++rk) mbar_arrive_cluster(mapa_u32(smem_u32(&empty_bar[s]), rk)); }
                     else mbar_arrive(&empty_bar[s]);
                     continue;
                 }
@@ -325,6 +338,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 }
                 // free the stage (in both CTAs of a pair) once these MMAs retire
                 if constexpr (kPair) umma_commit_pair(&empty_bar[s]);
+                else if (cm > 1) umma_commit_mc(&empty_bar[s], cmask);
                 else umma_commit(&empty_bar[s]);
             }
             if (g.dbg_stop == 2) {
@@ -545,7 +559,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     tc_fence_before();
     __syncthreads();
     if (tprobe && threadIdx.x == 0) g_foley_times[7] = clock64();
-    if constexpr (kPair) cluster_sync_all();   // the peer may still read this CTA's B half / signal its barriers
+    if (kPair || cm > 1) cluster_sync_all();   // the peers may still read this CTA's B half / signal its barriers
     if (warp == 1) {
         tc_fence_after();
         if constexpr (kPair) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);

@@ -163,6 +163,19 @@ inline int default_prefetch_distance() {
     return v;
 }
 
+// Weight-tile multicast across the m-tiles of a cluster (FOLEY_GEMM_MCAST = largest cluster size tried: 1 off, 2, 4).
+// Off by default: correct (bit-identical, tools/pair_check.py) but 2-8 % slower than plain tiles on every shape of the step in
+// both rounds (profiles/r02_mcast_check.log) although cuBLAS's kernels for these shapes all use 1x4 / 4x1 / 2x4 clusters.
+inline int default_mcast() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FOLEY_GEMM_MCAST");
+        v = e ? atoi(e) : 1;
+        if (v != 2 && v != 4) v = 1;
+    }
+    return v;
+}
+
 // CTA-pair tiles on by default (FOLEY_GEMM_PAIR=0 disables).
 inline int default_pair_mode() {
     static int v = -1;
@@ -183,6 +196,7 @@ struct GemmLaunch {
     int dbg_stop = 0;
     int prefetch_b = -1;       // -1: default distance
     int pair = -1;             // CTA-pair (cta_group::2) tiles: -1 default policy, 0 off, 1 on when the shape allows
+    int cluster_m = -1;        // weight-tile multicast across this many consecutive m-tiles: -1 default policy, 1 off, 2 / 4
     long long out_rows = 0;    // output rows per sample (0 -> a.rows); may exceed a.rows (halo rows read as zero)
     GemmEpi epi;
 };
@@ -192,7 +206,7 @@ inline cudaError_t launch_gemm_inst(const CUtensorMap& ma, const CUtensorMap& mb
                                     const GemmArgs& args, dim3 grid, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, kTF32, kPair>;
     auto kern = gemm_tcgen05_kernel<BN, kTF32, kPair>;
-    const int cx = kPair ? 2 : 1, cy = 1;
+    const int cx = kPair ? 2 : (args.cluster_m > 1 ? args.cluster_m : 1), cy = 1;
     static bool attr_set = false;
     if (!attr_set) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -263,13 +277,25 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
     // CTA-pair (cta_group::2) tiles: need an even number of m-tiles and a 128/256-wide tile
     int pair = L.pair >= 0 ? L.pair : default_pair_mode();
     if (mt % 2 != 0 || (L.bn != 256 && L.bn != 128) || (tf32 && L.bn != 256)) pair = 0;
+    // multicast clusters: cm consecutive m-tiles (grid.x) share every weight tile; bf16 single-CTA tiles only
+    int cm = L.cluster_m > 0 ? L.cluster_m : default_mcast();
+    if (pair || tf32 || L.bn < 128) cm = 1;
+    while (cm > 1 && mt % cm != 0) cm >>= 1;
+    {   // grids that go to the persistent kernel (below) keep whole-tile loads
+        static int persist_env = -1;
+        if (persist_env < 0) { const char* ev = getenv("FOLEY_GEMM_PERSIST"); persist_env = ev ? atoi(ev) : 1; }
+        int sms_ = 148;
+        const long long tiles_ = mt * nt * (L.splits < 1 ? 1 : L.splits);
+        const bool mode_ok_ = L.epi.mode == EPI_BF16 || L.epi.mode == EPI_SWIGLU || (L.epi.mode == EPI_F32 && persist_env >= 2);
+        if (persist_env && mode_ok_ && !tf32 && L.bn == 256 && !pair && tiles_ * 2 >= static_cast<long long>(sms_) * 3) cm = 1;
+    }
     const int cy = 1;
     CUtensorMap ma, mb;
     if (!encode_operand_map(&ma, L.a, 128 / cy, err)) return false;
     Operand wb;
     wb.ptr = L.w; wb.dtype = L.a.dtype; wb.k = L.a.k * L.taps; wb.rows = L.n; wb.batch = 1;
     wb.ld = wb.k; wb.batch_stride = wb.k * wb.rows;
-    if (!encode_operand_map(&mb, wb, pair ? L.bn / 2 : L.bn, err)) return false;
+    if (!encode_operand_map(&mb, wb, pair ? L.bn / 2 : L.bn / cm, err)) return false;
 
     const long long out_rows = L.out_rows > 0 ? L.out_rows : L.a.rows;
     CUtensorMap mc = ma;   // EPI_DAC stores directly; the DiT epilogues leave through TMA stores
@@ -292,6 +318,7 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
     args.dbg_stop = L.dbg_stop;
     args.prefetch_b = L.prefetch_b < 0 ? default_prefetch_distance() : L.prefetch_b;
     args.pf_mod = 1;
+    args.cluster_m = cm;
     const int m_tiles = static_cast<int>((out_rows + 127) / 128);
     dim3 grid(static_cast<unsigned>(m_tiles * (L.a.batch > 0 ? L.a.batch : 1)),
               static_cast<unsigned>(((nt + cy - 1) / cy) * cy), static_cast<unsigned>(args.splits));

@@ -1,5 +1,7 @@
 """What does cuBLAS (torch.matmul, bf16) achieve on the GEMM shapes of the XL step at M = 500?  Informational ceiling for
 csrc/gemm.cuh (library kernels are not on the product path).  CUDA-graph timing, 20 launches per graph."""
+import os
+
 import torch
 
 M = 500
@@ -11,6 +13,9 @@ for name, (K, N) in SHAPES.items():
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     torch.matmul(a, w.t(), out=out)
     torch.cuda.synchronize()
+    if os.environ.get("ONE_LAUNCH"):      # ncu target: which kernel does the library pick for this shape?
+        print(name, flush=True)
+        continue
     st = torch.cuda.Stream()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.stream(st):

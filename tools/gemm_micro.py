@@ -21,6 +21,7 @@ ap.add_argument("--iters", type=int, default=50)
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--all", action="store_true")
 ap.add_argument("--pair", type=int, default=-1, help="-1 default policy, 0 single-CTA tiles, 1 CTA-pair (cta_group::2) tiles")
+ap.add_argument("--mcast", type=int, default=0, help="weight-tile multicast over this many m-tiles (0 default policy, 1 off, 2, 4)")
 ap.add_argument("--sweep", action="store_true", help="every shape x {single, pair} x {full, TMA only, TMA+MMA} at --bn")
 ap.add_argument("--dbg", type=int, default=0, help="bring-up modes: 1 = setup only, 2 = TMA only, 3 = TMA+MMA (no epilogue), 4 = MMA only on a re-used "
                                                        "ring, 8 = full kernel + clock64 timeline of CTA 0")
@@ -56,7 +57,7 @@ def run(name, bn, pair=None, dbg=None):
     ldo = out.shape[-1]
 
     def launch():
-        s = lib.foley_gemm(x.data_ptr(), 0, B2, L, K, K, L * K, w.data_ptr(), N, taps, -(taps // 2), 1, sp, bn | (dbg << 16) | ((pair + 1) << 20), mode, 0,
+        s = lib.foley_gemm(x.data_ptr(), 0, B2, L, K, K, L * K, w.data_ptr(), N, taps, -(taps // 2), 1, sp, bn | (dbg << 16) | ((pair + 1) << 20) | (a.mcast << 22), mode, 0,
                            None, out.data_ptr(), ldo, L * ldo, B2 * L * ldo, None)
         assert s == 0, lib.foley_last_error()
 

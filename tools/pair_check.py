@@ -1,5 +1,6 @@
-"""CTA-pair (cta_group::2) GEMM tiles against single-CTA tiles through foley_gemm: same operands, every epilogue mode —
-the results must be bit-identical (same MMA shapes per row, same accumulation order), then timings of both.
+"""CTA-pair (cta_group::2) GEMM tiles and weight-tile multicast clusters (2 / 4 m-tiles) against plain single-CTA tiles
+through foley_gemm: same operands, every epilogue mode — the results must be bit-identical (same MMA shapes per row,
+same accumulation order), then timings of all of them.
     python tools/pair_check.py [--iters 200]
 """
 import argparse
@@ -31,7 +32,7 @@ for name, (K, taps, N, mode, sp) in SHAPES.items():
     w = (torch.randn(N, taps * K, device="cuda", generator=g) * 0.02).bfloat16()
     res = {}
     for bn in (256, 128):
-        for pair in (0, 1):
+        for pair, mc in ((0, 1), (0, 2), (0, 4), (1, 1)):
             if mode == 2:
                 out = torch.zeros(sp, B2, L, N, device="cuda", dtype=torch.float32)
             else:
@@ -40,11 +41,11 @@ for name, (K, taps, N, mode, sp) in SHAPES.items():
 
             def launch():
                 s = lib.foley_gemm(x.data_ptr(), 0, B2, L, K, K, L * K, w.data_ptr(), N, taps, -(taps // 2), 1, sp,
-                                   bn | ((pair + 1) << 20), mode, 0, None, out.data_ptr(), ldo, L * ldo, B2 * L * ldo, None)
+                                   bn | ((pair + 1) << 20) | (mc << 22), mode, 0, None, out.data_ptr(), ldo, L * ldo, B2 * L * ldo, None)
                 assert s == 0, lib.foley_last_error()
             launch()
             torch.cuda.synchronize()
-            res[(bn, pair)] = out.clone()
+            res[(bn, pair, mc)] = out.clone()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(a.iters):
@@ -53,9 +54,9 @@ for name, (K, taps, N, mode, sp) in SHAPES.items():
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / a.iters
             fl = 2.0 * B2 * L * K * taps * N
-            same = torch.equal(res[(bn, pair)], res[(bn, 0)])
+            same = torch.equal(res[(bn, pair, mc)], res[(bn, 0, 1)])
             ok_all &= same
-            print(f"{name:5s} K={K}x{taps} N={N} splits={sp} bn={bn} pair={pair}: {us:7.2f} us {fl / us / 1e6:7.1f} TFLOP/s"
-                  f"  {'bit-identical to single-CTA' if same else 'MISMATCH max|d|=%g' % (res[(bn, pair)].float() - res[(bn, 0)].float()).abs().max().item()}",
+            print(f"{name:5s} K={K}x{taps} N={N} splits={sp} bn={bn} pair={pair} mcast={mc}: {us:7.2f} us {fl / us / 1e6:7.1f} TFLOP/s"
+                  f"  {'bit-identical to plain tiles' if same else 'MISMATCH max|d|=%g' % (res[(bn, pair, mc)].float() - res[(bn, 0, 1)].float()).abs().max().item()}",
                   flush=True)
 print("PAIR_CHECK", "OK" if ok_all else "FAILED")
