@@ -352,7 +352,9 @@ def run_b200(args):
             sampler.join(timeout=3)
 
         # ================= end-to-end leg (`e2e`): public host API, host buffers =================
-        deps = cfgmod.AttributeDict({"dac_model": dac, "device": dev, "report_progress": False})
+        # progress reporting ON, as in the node's default: the engine publishes the step counter in mapped host memory and
+        # the calling thread polls it (no per-step stream synchronize); only rank 0's bar is driven in the product
+        deps = cfgmod.AttributeDict({"dac_model": dac, "device": dev, "report_progress": True})
         deps["foley_model"] = model
         h2d = sum(v.numel() * v.element_size() for v in feats.values()) + B * 128 * L * 2
         d2h = B * world * L * 960 * 4
@@ -622,17 +624,22 @@ def time_dominant_gemm(eng, c, B2, L, peaks):
     us = e0.elapsed_time(e1) * 1e3 / iters
     flops = 2.0 * B2 * L * 3 * C * 2 * Hs
     ach = flops / (us * 1e-6) / 1e12
-    traffic = None
+    # DRAM traffic per launch from the committed `ncu --set full` capture of this kernel; the capture names the source hash of
+    # the build it profiled, so a stale number is visible (traffic_build != this build)
+    traffic, traffic_build = None, None
     prof = os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            traffic, traffic_build = pj.get("dram_bytes_per_launch"), pj.get("src_hash")
         except Exception:
             traffic = None
+    this_build = lib.foley_version().decode().rsplit("src:", 1)[-1]
     return {"kernel": f"gemm_tcgen05_kernel<{bn},bf16> single-block ConvMLP w1|w3 conv(k=3)+SwiGLU", "bound": "tensor",
             "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
             "peak_source": peaks["_source"] + " burst", "us_per_launch": us, "flops_per_launch": flops,
-            "traffic": traffic}
+            "traffic": traffic, "traffic_build": traffic_build, "this_build": this_build,
+            "algorithmic_bytes": 2.0 * (2 * Hs * 3 * C + B2 * L * C + B2 * L * Hs)}
 
 
 def main():
