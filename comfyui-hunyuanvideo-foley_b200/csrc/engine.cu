@@ -107,6 +107,7 @@ foley_status Engine::create(const foley_config* c, int dev) {
         FOLEY_CUDA_OK(cudaFuncSetAttribute(attention_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<4, 4>::SMEM));
         FOLEY_CUDA_OK(cudaFuncSetAttribute(attention_kernel<8, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<8, 3, 2>::SMEM));
         if (const char* e = getenv("FOLEY_ATT_KVSPLIT")) att_kv_split = atoi(e) != 0;
+        if (const char* e = getenv("FOLEY_SIDE_SPLITS")) side_split_cap = atoi(e);
         if (const char* e = getenv("FOLEY_ATT_TC")) att_tc = atoi(e);
         if (const char* e = getenv("FOLEY_ATT_FUSED")) att_fused = atoi(e) != 0;
         FOLEY_CUDA_OK(attention_tc_init());
@@ -533,7 +534,7 @@ foley_status Engine::proj_combine(cudaStream_t st, const bf16* A, int rows, int 
                                   const LinearW& W, float* partials, CombineArgs ca) {
     const int kblocks = W.k * W.taps / 64;
     int bn = 128, splits = 1;
-    plan_gemm(rows, batch, W.n, kblocks, true, &bn, &splits);
+    plan_gemm(rows, batch, W.n, kblocks, true, &bn, &splits, st == side_stream ? side_split_cap : 0);
     GemmEpi e;
     e.mode = EPI_F32;
     e.out = partials;
@@ -867,7 +868,9 @@ foley_status Engine::step(cudaStream_t st) {
     auto qkv_gemm = [&](cudaStream_t s_, const bf16* A, int rows, int batch, const LinearW& W, int n_cols, float* partials,
                         int part_cols, bf16* out_bf16, QkvArgs* q) -> foley_status {
         int bn = 128, splits = 1;
-        plan_gemm(rows, batch, n_cols, W.k / 64, qkv_split, &bn, &splits, max_splits * part_cols / n_cols);   // workspace cap
+        int cap_ = max_splits * part_cols / n_cols;   // workspace cap
+        if (s_ == side_stream && side_split_cap > 0) cap_ = std::min(cap_, side_split_cap);
+        plan_gemm(rows, batch, n_cols, W.k / 64, qkv_split, &bn, &splits, cap_);
         const long long a_bs = static_cast<long long>(rows) * C;
         if (splits > 1) {
             GemmEpi e;

@@ -130,6 +130,8 @@ class Engine {
     // grid and repeated per query tile: +7 us per call, step 4.51 ms.
     int att_tc = -1;
     bool att_fused = false;
+    int side_split_cap = 0;              // > 0: cap on the K splits of the visual-branch GEMMs (FOLEY_SIDE_SPLITS): they run beside the
+                                         // audio-stream GEMMs and every CTA they occupy is taken from those
     bool mod_on_branch = false;          // measured: no gain (the GEMM saturates the SMs either way)
     // planner cost model (us): a k-block costs the same for every tile width (one tcgen05.mma ~150 cycles whatever N), so
     // wide tiles + more K-splits win whenever they fit the SMs (measured: tools/gemm_micro.py --dbg 4, FOLEY_PLAN sweeps)
