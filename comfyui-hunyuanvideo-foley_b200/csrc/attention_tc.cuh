@@ -2,7 +2,7 @@
 // operand load: replaces, per call, qk_norm_rope_kernel + attention_kernel (attn_layers.py:323-456 joint self-attention
 // and cross-attention to the text tokens, hifi_foley.py:364-390 single-stream self-attention).
 //
-// One CTA = 128 query rows of one (sample, head), 16 warps.  Per chunk of keys (the whole sequence when it has <= 320 keys
+// One CTA = 128 query rows of one (sample, head), 12 warps in three roles (softmax, O accumulation, copy / MMA issue).  Per chunk of keys (the whole sequence when it has <= 320 keys
 // — every shape of a 5 s clip — else 128 keys at a time, double-buffered, with the online-softmax rescale):
 //   load   single threads issue TMA boxes (128-160 rows x 64 channels, 128-byte swizzle = the canonical tcgen05 operand layout)
 //          straight from the projection GEMM's bf16 output (or from prepared [B,H,S,128] tensors); rows past the end of
@@ -47,7 +47,12 @@ struct AttTcArgs {
 
 constexpr int ATC_CK = 320;                          // short mode: the whole sequence (<= 320 keys) is one resident chunk
 constexpr int ATC_CK_LONG = 128;                     // long mode: 128-key chunks, double-buffered (the next chunk lands under this one's math)
-constexpr int ATC_THREADS = 512;                     // 16 warps: four per TMEM lane quarter, splitting the columns
+constexpr int ATC_CS = 2;                            // softmax column shares: softmax warps per TMEM lane quarter
+constexpr int ATC_SOFTMAX = 128 * ATC_CS;            // warps 0..7: S -> P (a thread owns a row and 1/ATC_CS of its columns)
+constexpr int ATC_CORR = 128;                        // warps 8..11: O accumulation (a thread owns a row and all 128 channels);
+                                                     // lane 0 of warp 8 also issues every TMA copy and every MMA
+constexpr int ATC_WORKERS = ATC_SOFTMAX;             // threads of the in-place norm pass
+constexpr int ATC_THREADS = ATC_SOFTMAX + ATC_CORR;  // 384: register files are handed out per 4 warps — 168 registers each
 constexpr int ATC_BOX_Q = 128;                       // rows per TMA box: the Q tile is one box per d half,
 constexpr int ATC_BOX_KV_SHORT = 160;                // a resident K / V tile at most two (a TMA instruction costs its issuing
 constexpr int ATC_BOX_KV_LONG = 128;                 // thread ~60 ns: few big boxes), a 128-key chunk one
@@ -56,7 +61,7 @@ constexpr int ATC_KV_BYTES = 2 * ATC_CK * 128;       // short mode: two d halves
 constexpr int ATC_LONG_STAGE = 2 * (2 * ATC_CK_LONG * 128);   // long mode: K + V of one 128-key chunk = 64 KB; P behind the two stages
 constexpr int ATC_O_COL = 384;                       // TMEM: S columns [0, 320), O columns [384, 512)
 constexpr int ATC_O_PITCH = 272;                     // output staging: 256 B per row + 16 B (conflict-free both ways)
-constexpr int ATC_SMEM = 1024 + ATC_Q_BYTES + 2 * ATC_KV_BYTES + 8 * 128 * 4 + 128;
+constexpr int ATC_SMEM = 1024 + ATC_Q_BYTES + 2 * ATC_KV_BYTES + 12 * 128 * 4 + 128;   // (barriers: 9 x 8 bytes + the TMEM slot)
 
 __device__ __forceinline__ float ex2_fast(float x) {
     float y;
@@ -96,7 +101,7 @@ __device__ __forceinline__ void atc_norm_rows(const AttNorm& nm, int row0, int n
     uint4 wr0 = make_uint4(0u, 0u, 0u, 0u), wr1 = wr0;
     if (nm.w[0]) wr0 = *reinterpret_cast<const uint4*>(nm.w[0] + sub * 8);
     if (nm.w[1]) wr1 = *reinterpret_cast<const uint4*>(nm.w[1] + sub * 8);
-    constexpr int RSTEP = ATC_THREADS / 16;
+    constexpr int RSTEP = ATC_WORKERS / 16;
     for (int rb = threadIdx.x >> 4; rb < n_rows; rb += RSTEP * ATC_NB) {   // (trip counts are warp-uniform: n_rows % 16 == 0)
         float4 t0[ATC_NB], t1[ATC_NB];
         bool normed[ATC_NB], seg1[ATC_NB];
@@ -172,6 +177,49 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, 
     return d;
 }
 
+// exponentials of one 32-column group of a row (scaled log2 domain), packed to bf16 pairs; returns the fp32 row-sum share
+__device__ __forceinline__ float atc_exps(const uint32_t (&v)[32], uint32_t (&pk)[16], int c0, int kn, float scale_log2, float m_new) {
+    float l = 0.f;
+    if (c0 + 32 <= kn) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2_fast(fmaf(__uint_as_float(v[j]), scale_log2, -m_new));
+            const float p1 = ex2_fast(fmaf(__uint_as_float(v[j + 1]), scale_log2, -m_new));
+            l += p0 + p1;
+            pk[j >> 1] = pack_bf16x2(p0, p1);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const float p0 = (c0 + j) < kn ? ex2_fast(fmaf(__uint_as_float(v[j]), scale_log2, -m_new)) : 0.f;
+            const float p1 = (c0 + j + 1) < kn ? ex2_fast(fmaf(__uint_as_float(v[j + 1]), scale_log2, -m_new)) : 0.f;
+            l += p0 + p1;
+            pk[j >> 1] = pack_bf16x2(p0, p1);
+        }
+    }
+    return l;
+}
+// o_acc = o_acc * corr + O chunk read back from TMEM (this thread's channels)
+template <int N>
+__device__ __forceinline__ void atc_take_o(float (&o_acc)[N], uint32_t taddr, float corr) {
+#pragma unroll
+    for (int g = 0; g < N / 32; ++g) {
+        uint32_t ov[32];
+        tmem_ld_32x32(taddr + g * 32, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o_acc[g * 32 + j] = fmaf(o_acc[g * 32 + j], corr, __uint_as_float(ov[j]));
+    }
+}
+// 32 bf16 of row `row`, columns [c0, c0 + 32), into the K-major swizzled P tile
+__device__ __forceinline__ void atc_put(const uint32_t (&pk)[16], uint32_t sP, int row, int c0) {
+    const uint32_t blk = static_cast<uint32_t>(c0 >> 6), ch0 = static_cast<uint32_t>((c0 & 63) >> 3);
+    const uint32_t base = sP + blk * 16384u + static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        st_shared_v4(base + (((ch0 + j) ^ static_cast<uint32_t>(row & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+}
+
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const AttTcArgs a) {
@@ -179,17 +227,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sQ = smem_u32(smem);
     const uint32_t sR = sQ + ATC_Q_BYTES;           // K / V / P region (160 KB)
-    float* red = reinterpret_cast<float*>(smem + ATC_Q_BYTES + 2 * ATC_KV_BYTES);   // [4][128] max, [4][128] sum
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_Q_BYTES + 2 * ATC_KV_BYTES + 8 * 128 * 4);
-    uint64_t* full_k = bars;            // [2]
-    uint64_t* full_v = bars + 2;        // [2]
-    uint64_t* bar_s = bars + 4;
-    uint64_t* bar_o = bars + 5;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    float* red_all = reinterpret_cast<float*>(smem + ATC_Q_BYTES + 2 * ATC_KV_BYTES);   // [2 chunks][2 shares][128] partial row maxima,
+    float* red_sum = red_all + 512;                 // [2 shares][128] row-sum shares,
+    float* corr_s = red_all + 768;                  // [4 chunks][128] correction factor of chunk c for every row
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_Q_BYTES + 2 * ATC_KV_BYTES + 12 * 128 * 4);
+    uint64_t* full_k = bars;            // [2]  K (+ Q) of a stage has landed
+    uint64_t* full_v = bars + 2;        // [2]  V of a stage has landed
+    uint64_t* bar_s = bars + 4;         // [2]  S(c) is complete in TMEM buffer c & 1
+    uint64_t* bar_o = bars + 6;         //      PV(c) is complete (O chunk in TMEM; P and the V tile are free)
+    uint64_t* p_ready = bars + 7;       //      every softmax thread has written its share of P(c) (and has read S(c))
+    uint64_t* o_free = bars + 8;        //      every accumulation thread has read the O chunk
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool softmax_role = warp < ATC_SOFTMAX / 32;
+    const bool control = threadIdx.x == ATC_SOFTMAX;      // lane 0 of the first accumulation warp
     const int qq = warp & 3;            // TMEM lane quarter
-    const int cs = warp >> 2;           // which share of the columns (0..3)
+    const int cs = (warp >> 2) & (ATC_CS - 1);   // softmax: which share of the columns
     const int row = qq * 32 + lane;     // query row of the tile (= TMEM lane)
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
 
@@ -200,6 +254,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int cap = long_mode ? ATC_CK_LONG : ATC_CK;      // rows per d-half block of a K / V tile
     const int n_chunks = (a.Sk + ck - 1) / ck;
     const uint32_t sP = long_mode ? sR + 2 * ATC_LONG_STAGE : sR;   // short mode: P aliases the (dead) K tile
+    const uint32_t s_col = long_mode ? 128u : 0u;          // long mode: S(c) lives in TMEM columns [(c & 1) * 128, +128)
     auto k_tile = [&](int c) { return long_mode ? sR + static_cast<uint32_t>(c & 1) * ATC_LONG_STAGE : sR; };
     auto v_tile = [&](int c) { return long_mode ? sR + static_cast<uint32_t>(c & 1) * ATC_LONG_STAGE + 2 * ATC_CK_LONG * 128 : sR + ATC_KV_BYTES; };
     auto chunk_rows = [&](int c) { return (min(ck, a.Sk - c * ck) + 15) & ~15; };
@@ -210,9 +265,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_k);
         tma_prefetch_desc(&tm_v);
-        for (int i = 0; i < 2; ++i) { mbar_init(&full_k[i], 1); mbar_init(&full_v[i], 1); }
-        mbar_init(bar_s, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&full_k[i], 1); mbar_init(&full_v[i], 1); mbar_init(&bar_s[i], 1); }
         mbar_init(bar_o, 1);
+        mbar_init(p_ready, ATC_SOFTMAX);
+        mbar_init(o_free, ATC_CORR);
         fence_barrier_init();
     }
     tc_fence_before();
@@ -227,183 +283,229 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     if (a.kv_batch_map) kb = a.kv_batch_map[a.grp_of_sample ? a.grp_of_sample[b] : b];
     if (probe0) g_foley_times[1] = clock64();
 
-    // The copies and the MMAs are issued by lane 0 of three different warps (K + Q: warp 1, V: warp 2, MMA: warp 0), so that
-    // no softmax warp is held up by all of them.
-    const int box_kv = long_mode ? ATC_BOX_KV_LONG : ATC_BOX_KV_SHORT;
-    auto issue_k = [&](int c) {         // thread 32: K of chunk c (with Q for the first chunk)
-        const int st = c & 1, rows = chunk_rows(c);
-        mbar_expect_tx(&full_k[st], atc_tile_bytes(rows, box_kv) + (c == 0 ? atc_tile_bytes(128, ATC_BOX_Q) : 0u));
-        if (c == 0) atc_issue_tile(&tm_q, &full_k[0], b, h, q0, 128, ATC_BOX_Q, sQ, 128);
-        atc_issue_tile(&tm_k, &full_k[st], kb, h, c * ck, rows, box_kv, k_tile(c), cap);
-    };
-    auto issue_v = [&](int c) {         // thread 64: V of chunk c
-        const int st = c & 1, rows = chunk_rows(c);
-        mbar_expect_tx(&full_v[st], atc_tile_bytes(rows, box_kv));
-        atc_issue_tile(&tm_v, &full_v[st], kb, h, c * ck, rows, box_kv, v_tile(c), cap);
-    };
-    auto issue_s = [&](int c) {         // thread 0: S = Q K(c)^T; more than 256 keys: two MMAs of about half the columns each
-        const int kpad = chunk_rows(c);     // (an MMA costs max(69, N/2) cycles: 160 + 144 columns beat 256 + 48)
-        const int n_first = kpad <= 256 ? kpad : ((kpad + 31) >> 5) << 4;
-        for (int n_off = 0; n_off < kpad; n_off += n_first) {
-            const int n = min(n_first, kpad - n_off);
-            const uint32_t idesc = make_idesc(1, 128, n);
+    if (softmax_role) {
+        // ================================================================== 8 softmax warps: (norm,) S -> P
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+            float* red = red_all + (c & 1) * 256;     // (double-buffered: a fast thread's chunk c+1 never meets a slow reader of chunk c)
+            auto row_max = [&]() {   // max over the shares' partial maxima of this row
+                float m = red[row];
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const uint64_t a_desc = make_smem_desc_sw128(sQ + (ks >> 2) * 16384 + (ks & 3) * 32);
-                const uint64_t b_desc = make_smem_desc_sw128(k_tile(c) + (ks >> 2) * (cap * 128) + n_off * 128 + (ks & 3) * 32);
-                umma_bf16(tmem_base + n_off, a_desc, b_desc, idesc, ks != 0);
+                for (int i = 1; i < ATC_CS; ++i) m = fmaxf(m, red[i * 128 + row]);
+                return m;
+            };
+            const int key0 = c * ck;
+            const int kn = min(ck, a.Sk - key0);
+            const int kpad = (kn + 15) & ~15;
+            const bool probe = probe0 && c == a.probe_chunk;
+            if (probe) g_foley_times[2] = clock64();
+            if (c == 0 || k_normed) {
+                mbar_wait(&full_k[c & 1], (c >> 1) & 1, 0x610 + c);
+                if (probe) g_foley_times[3] = clock64();
+                if (c == 0) atc_norm_rows(a.qn, q0, 128, a.Sq, sQ, 128, a.norm_kind, a.eps);
+                atc_norm_rows(a.kn, key0, kpad, a.Sk, k_tile(c), cap, a.norm_kind, a.eps);
+                fence_proxy_async();
+                asm volatile("bar.sync 2, %0;" ::"n"(ATC_SOFTMAX + 32) : "memory");   // + the control warp
             }
-        }
-        umma_commit(bar_s);
-    };
-    if (threadIdx.x == 32) issue_k(0);
-    if (threadIdx.x == 64) issue_v(0);
+            if (probe) g_foley_times[4] = clock64();
+            mbar_wait(&bar_s[c & 1], (c >> 1) & 1, 0x600 + c);
+            tc_fence_after();
+            if (probe) g_foley_times[5] = clock64();
 
-    float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[32];
+            // ---- softmax of this thread's row over its share of the 32-column groups
+            const uint32_t s_row = t_row + static_cast<uint32_t>(c & 1) * s_col;
+            const int n_grp = (kpad + 31) >> 5;
+            const int g_lo = (n_grp * cs) / ATC_CS, g_hi = (n_grp * (cs + 1)) / ATC_CS;
+            float l_chunk = 0.f;
+            float corr;
+            if (long_mode) {
+                // at most two groups (128 keys / 32 / ATC_CS): S is read once and stays in registers; the exponentials are
+                // computed before PV(c-1) is waited for, P is written after it (one P buffer)
+                uint32_t va[32], vb[32], pka[16], pkb[16];
+                const bool has_a = g_lo < g_hi, has_b = g_lo + 1 < g_hi;
+                float mx = -INFINITY;
+                if (has_a) tmem_ld_32x32(s_row + g_lo * 32, va);
+                if (has_b) tmem_ld_32x32(s_row + (g_lo + 1) * 32, vb);
+                tmem_ld_wait();
+                if (has_a) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o_acc[j] = 0.f;
-
-    for (int c = 0; c < n_chunks; ++c) {
-        const int key0 = c * ck;
-        const int kn = min(ck, a.Sk - key0);
-        const int kpad = (kn + 15) & ~15;
-        const bool probe = probe0 && c == a.probe_chunk;
-        if (probe) g_foley_times[2] = clock64();
-        // prefetch the next chunk into the other stage: its previous contents (chunk c-1) are dead — S(c-1) and PV(c-1)
-        // have completed (every thread waited on bar_o) and the norm pass of that stage is behind several barriers
-        if (c + 1 < n_chunks) {
-            if (threadIdx.x == 32) issue_k(c + 1);
-            if (threadIdx.x == 64) issue_v(c + 1);
-        }
-        if (c == 0 || k_normed) {
-            // S(c) was not issued ahead: Q / K(c) must be normalised first (or this is the first chunk)
-            mbar_wait(&full_k[c & 1], (c >> 1) & 1, 0x610 + c);
-            if (probe) g_foley_times[3] = clock64();
-            if (c == 0) atc_norm_rows(a.qn, q0, 128, a.Sq, sQ, 128, a.norm_kind, a.eps);
-            atc_norm_rows(a.kn, key0, kpad, a.Sk, k_tile(c), cap, a.norm_kind, a.eps);
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (g_lo * 32 + j) < kn ? __uint_as_float(va[j]) : -INFINITY);
+                }
+                if (has_b) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((g_lo + 1) * 32 + j) < kn ? __uint_as_float(vb[j]) : -INFINITY);
+                }
+                red[cs * 128 + row] = mx;
+                asm volatile("bar.sync 1, %0;" ::"n"(ATC_SOFTMAX) : "memory");
+                if (probe) g_foley_times[6] = clock64();
+                const float m_new = fmaxf(m_run, row_max() * a.scale_log2);
+                corr = ex2_fast(m_run - m_new);     // first chunk: exp2(-inf) = 0
+                m_run = m_new;
+                if (cs == 0) corr_s[(c & 3) * 128 + row] = corr;    // for the accumulation warps (read after PV(c) completes)
+                if (has_a) l_chunk += atc_exps(va, pka, g_lo * 32, kn, a.scale_log2, m_new);
+                if (has_b) l_chunk += atc_exps(vb, pkb, (g_lo + 1) * 32, kn, a.scale_log2, m_new);
+                if (c > 0) mbar_wait(bar_o, (c - 1) & 1, 0x680 + c);   // PV(c-1), which ran under the lines above, frees the P buffer
+                if (has_a) atc_put(pka, sP, row, g_lo * 32);
+                if (has_b) atc_put(pkb, sP, row, (g_lo + 1) * 32);
+            } else {
+                // one resident chunk of up to 320 keys: two passes over S (max, then exponentials), no rescale at all
+                uint32_t v[32], pk[16];
+                float mx = -INFINITY;
+                for (int g = g_lo; g < g_hi; ++g) {
+                    tmem_ld_32x32(s_row + g * 32, v);
+                    tmem_ld_wait();
+                    const int c0 = g * 32;
+                    if (c0 + 32 <= kn) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c0 + j) < kn ? __uint_as_float(v[j]) : -INFINITY);
+                    }
+                }
+                red[cs * 128 + row] = mx;
+                asm volatile("bar.sync 1, %0;" ::"n"(ATC_SOFTMAX) : "memory");
+                if (probe) g_foley_times[6] = clock64();
+                const float m_new = fmaxf(m_run, row_max() * a.scale_log2);
+                corr = ex2_fast(m_run - m_new);
+                m_run = m_new;
+                if (cs == 0) corr_s[(c & 3) * 128 + row] = corr;
+                for (int g = g_lo; g < g_hi; ++g) {
+                    tmem_ld_32x32(s_row + g * 32, v);
+                    tmem_ld_wait();
+                    l_chunk += atc_exps(v, pk, g * 32, kn, a.scale_log2, m_new);
+                    atc_put(pk, sP, row, g * 32);
+                }
+            }
+            l_run = l_run * corr + l_chunk;
+            if (c + 1 == n_chunks) red_sum[cs * 128 + row] = l_run;   // final row-sum shares (read behind barrier 3)
+            if (probe) g_foley_times[7] = clock64();
             fence_proxy_async();
             tc_fence_before();
-            __syncthreads();
-            tc_fence_after();
-            if (threadIdx.x == 0) issue_s(c);
+            mbar_arrive(p_ready);
+            if (probe) g_foley_times[8] = clock64();
         }
-        if (probe) g_foley_times[4] = clock64();
-        mbar_wait(bar_s, c & 1, 0x600 + c);
-        tc_fence_after();
-        if (probe) g_foley_times[5] = clock64();
-
-        // ---- softmax of this thread's row over its share of the 32-column groups
-        const int n_grp = (kpad + 31) >> 5;
-        const int g_lo = (n_grp * cs) >> 2, g_hi = (n_grp * (cs + 1)) >> 2;
-        uint32_t v[32];
-        float mx = -INFINITY;
-        for (int g = g_lo; g < g_hi; ++g) {
-            tmem_ld_32x32(t_row + g * 32, v);
-            tmem_ld_wait();
-            const int c0 = g * 32;
-            if (c0 + 32 <= kn) {
+    } else {
+        // ================================================================== 4 accumulation warps (+ copy / MMA issue by lane 0 of warp 8)
+        const int box_kv = long_mode ? ATC_BOX_KV_LONG : ATC_BOX_KV_SHORT;
+        auto issue_k = [&](int c) {         // K of chunk c (with Q for the first chunk) -> stage c & 1
+            const int st = c & 1, rows = chunk_rows(c);
+            mbar_expect_tx(&full_k[st], atc_tile_bytes(rows, box_kv) + (c == 0 ? atc_tile_bytes(128, ATC_BOX_Q) : 0u));
+            if (c == 0) atc_issue_tile(&tm_q, &full_k[0], b, h, q0, 128, ATC_BOX_Q, sQ, 128);
+            atc_issue_tile(&tm_k, &full_k[st], kb, h, c * ck, rows, box_kv, k_tile(c), cap);
+        };
+        auto issue_v = [&](int c) {
+            const int st = c & 1, rows = chunk_rows(c);
+            mbar_expect_tx(&full_v[st], atc_tile_bytes(rows, box_kv));
+            atc_issue_tile(&tm_v, &full_v[st], kb, h, c * ck, rows, box_kv, v_tile(c), cap);
+        };
+        auto issue_s = [&](int c) {         // S(c) = Q K(c)^T; more than 256 keys: two MMAs of about half the columns each
+            const int kpad = chunk_rows(c);     // (an MMA costs max(69, N/2) cycles: 160 + 144 columns beat 256 + 48)
+            const int n_first = kpad <= 256 ? kpad : ((kpad + 31) >> 5) << 4;
+            const uint32_t d0 = tmem_base + static_cast<uint32_t>(c & 1) * s_col;
+            for (int n_off = 0; n_off < kpad; n_off += n_first) {
+                const int n = min(n_first, kpad - n_off);
+                const uint32_t idesc = make_idesc(1, 128, n);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c0 + j) < kn ? __uint_as_float(v[j]) : -INFINITY);
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint64_t a_desc = make_smem_desc_sw128(sQ + (ks >> 2) * 16384 + (ks & 3) * 32);
+                    const uint64_t b_desc = make_smem_desc_sw128(k_tile(c) + (ks >> 2) * (cap * 128) + n_off * 128 + (ks & 3) * 32);
+                    umma_bf16(d0 + n_off, a_desc, b_desc, idesc, ks != 0);
+                }
             }
+            umma_commit(&bar_s[c & 1]);
+        };
+        if (control) {
+            issue_k(0);
+            issue_v(0);
+            if (n_chunks > 1) { issue_k(1); issue_v(1); }
         }
-        red[cs * 128 + row] = mx;
-        __syncthreads();
-        if (probe) g_foley_times[6] = clock64();
-        const float m_chunk = fmaxf(fmaxf(red[row], red[128 + row]), fmaxf(red[256 + row], red[384 + row])) * a.scale_log2;
-        const float m_new = fmaxf(m_run, m_chunk);
-        const float corr = ex2_fast(m_run - m_new);     // first chunk: exp2(-inf) = 0
-        m_run = m_new;
-        float l_chunk = 0.f;
-        for (int g = g_lo; g < g_hi; ++g) {
-            if (g_hi - g_lo > 1) {                       // (a single group is still in registers from the max pass)
-                tmem_ld_32x32(t_row + g * 32, v);
+        float o_acc[128];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) o_acc[j] = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+            if (warp == ATC_SOFTMAX / 32) {
+                if (c == 0 || k_normed) {
+                    // Q / K(c) are normalised in place by the softmax warps first (or this is the first chunk): they meet this warp here
+                    asm volatile("bar.sync 2, %0;" ::"n"(ATC_SOFTMAX + 32) : "memory");
+                    if (control) {
+                        tc_fence_after();
+                        mbar_wait(&full_k[c & 1], (c >> 1) & 1, 0x610 + c);
+                        issue_s(c);
+                        if (c == 0 && !k_normed && n_chunks > 1) {      // K needs no norm pass: S runs two chunks ahead
+                            mbar_wait(&full_k[1], 0, 0x611);
+                            tc_fence_after();
+                            issue_s(1);
+                        }
+                    }
+                }
+                if (control) {
+                    const int kpad = chunk_rows(c);
+                    // refills first (nothing here blocks): V(c+1) into the stage PV(c-1) has released (this warp waited on it in
+                    // the previous iteration), K(c+2) into the stage S(c) has released
+                    if (c >= 1 && c + 1 < n_chunks) issue_v(c + 1);
+                    if (c + 2 < n_chunks) {
+                        mbar_wait(&bar_s[c & 1], (c >> 1) & 1, 0x670 + c);
+                        issue_k(c + 2);
+                    }
+                    mbar_wait(p_ready, c & 1, 0x640 + c);               // P(c) written, S(c) consumed by every softmax thread
+                    if (c > 0) mbar_wait(o_free, (c - 1) & 1, 0x660 + c);   // O(c-1) read by every accumulation thread
+                    mbar_wait(&full_v[c & 1], (c >> 1) & 1, 0x620 + c);
+                    tc_fence_after();
+                    // ---- O_chunk = P V: K = kpad keys in steps of 16, N = 128 (d), V MN-major
+                    const uint32_t idesc = make_idesc(1, 128, 128) | (1u << 16);
+                    for (int kk = 0; kk < (kpad >> 4); ++kk) {
+                        const uint64_t a_desc = make_smem_desc_sw128(sP + (kk >> 2) * 16384 + (kk & 3) * 32);
+                        const uint64_t b_desc = make_smem_desc_mn_sw128(v_tile(c) + kk * 2048, static_cast<uint32_t>(cap * 128), 1024u);
+                        umma_bf16(tmem_base + ATC_O_COL, a_desc, b_desc, idesc, kk != 0);
+                    }
+                    umma_commit(bar_o);
+                    if (c + 2 < n_chunks && !k_normed) {                // S runs two chunks ahead: TMEM buffer c & 1 is free (p_ready(c))
+                        mbar_wait(&full_k[c & 1], ((c + 2) >> 1) & 1, 0x630 + c);
+                        tc_fence_after();
+                        issue_s(c + 2);
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- o_acc = o_acc * corr(c) + O chunk (this thread's row, all 128 channels), 16 columns at a time
+            mbar_wait(bar_o, c & 1, 0x6a0 + c);
+            tc_fence_after();
+            const float corr = corr_s[(c & 3) * 128 + row];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                uint32_t ov[16];
+                tmem_ld_32x16(t_row + ATC_O_COL + g * 16, ov);
                 tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o_acc[g * 16 + j] = fmaf(o_acc[g * 16 + j], corr, __uint_as_float(ov[j]));
             }
-            const int c0 = g * 32;
-            uint32_t pk[16];
-            if (c0 + 32 <= kn) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float p0 = ex2_fast(fmaf(__uint_as_float(v[j]), a.scale_log2, -m_new));
-                    const float p1 = ex2_fast(fmaf(__uint_as_float(v[j + 1]), a.scale_log2, -m_new));
-                    l_chunk += p0 + p1;
-                    pk[j >> 1] = pack_bf16x2(p0, p1);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float p0 = (c0 + j) < kn ? ex2_fast(fmaf(__uint_as_float(v[j]), a.scale_log2, -m_new)) : 0.f;
-                    const float p1 = (c0 + j + 1) < kn ? ex2_fast(fmaf(__uint_as_float(v[j + 1]), a.scale_log2, -m_new)) : 0.f;
-                    l_chunk += p0 + p1;
-                    pk[j >> 1] = pack_bf16x2(p0, p1);
-                }
-            }
-            const uint32_t blk = static_cast<uint32_t>(c0 >> 6), ch0 = static_cast<uint32_t>((c0 & 63) >> 3);
-            const uint32_t base = sP + blk * 16384u + static_cast<uint32_t>(row) * 128u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                st_shared_v4(base + (((ch0 + j) ^ static_cast<uint32_t>(row & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            tc_fence_before();
+            mbar_arrive(o_free);
         }
-        l_run = l_run * corr + l_chunk;
-        if (c + 1 == n_chunks) red[512 + cs * 128 + row] = l_run;   // final row-sum shares: visible after the barrier below
-        if (probe) g_foley_times[7] = clock64();
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (probe) g_foley_times[8] = clock64();
-        if (threadIdx.x == 0) {
-            // ---- O_chunk = P V: K = kpad keys in steps of 16, N = 128 (d), V MN-major
-            mbar_wait(&full_v[c & 1], (c >> 1) & 1, 0x620 + c);
-            tc_fence_after();
-            const uint32_t idesc = make_idesc(1, 128, 128) | (1u << 16);
-            for (int kk = 0; kk < (kpad >> 4); ++kk) {
-                const uint64_t a_desc = make_smem_desc_sw128(sP + (kk >> 2) * 16384 + (kk & 3) * 32);
-                const uint64_t b_desc = make_smem_desc_mn_sw128(v_tile(c) + kk * 2048, static_cast<uint32_t>(cap * 128), 1024u);
-                umma_bf16(tmem_base + ATC_O_COL, a_desc, b_desc, idesc, kk != 0);
-            }
-            umma_commit(bar_o);
-            // the S region is free (every thread's reads of S(c) are behind the barrier above): when K needs no norm pass,
-            // S(c+1) goes out right behind PV(c) and runs under the O read-back of this chunk
-            if (!k_normed && c + 1 < n_chunks) {
-                mbar_wait(&full_k[(c + 1) & 1], ((c + 1) >> 1) & 1, 0x630 + c);
-                tc_fence_after();
-                issue_s(c + 1);
-            }
+        // ---- normalise by the row sum (all softmax shares) and stage the bf16 row in the dead Q / K memory
+        if (probe0) g_foley_times[9] = clock64();
+        asm volatile("bar.sync 3, %0;" ::"n"(ATC_THREADS) : "memory");   // row-sum shares visible; every MMA has completed
+        {
+            float lsum = red_sum[row];
+#pragma unroll
+            for (int i = 1; i < ATC_CS; ++i) lsum += red_sum[i * 128 + row];
+            const float inv = __fdividef(1.0f, lsum);
+            const uint32_t dst = sQ + static_cast<uint32_t>(row) * ATC_O_PITCH;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                st_shared_v4(dst + j * 16, pack_bf16x2(o_acc[8 * j] * inv, o_acc[8 * j + 1] * inv),
+                             pack_bf16x2(o_acc[8 * j + 2] * inv, o_acc[8 * j + 3] * inv),
+                             pack_bf16x2(o_acc[8 * j + 4] * inv, o_acc[8 * j + 5] * inv),
+                             pack_bf16x2(o_acc[8 * j + 6] * inv, o_acc[8 * j + 7] * inv));
         }
-        mbar_wait(bar_o, c & 1, 0x680 + c);
-        tc_fence_after();
-        if (probe) g_foley_times[9] = clock64();
-        tmem_ld_32x32(t_row + ATC_O_COL + cs * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o_acc[j] = fmaf(o_acc[j], corr, __uint_as_float(v[j]));
-        if (probe) g_foley_times[10] = clock64();
     }
-    if (probe0) g_foley_times[11] = clock64();
-
-    // ---- normalise by the row sum (all four column shares), stage the bf16 tile in the dead Q / K memory, store whole rows
-    {
-        const float inv = __fdividef(1.0f, (red[512 + row] + red[512 + 128 + row]) + (red[512 + 256 + row] + red[512 + 384 + row]));
-        const uint32_t dst = sQ + static_cast<uint32_t>(row) * ATC_O_PITCH + static_cast<uint32_t>(cs) * 64u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            st_shared_v4(dst + j * 16, pack_bf16x2(o_acc[8 * j] * inv, o_acc[8 * j + 1] * inv),
-                         pack_bf16x2(o_acc[8 * j + 2] * inv, o_acc[8 * j + 3] * inv),
-                         pack_bf16x2(o_acc[8 * j + 4] * inv, o_acc[8 * j + 5] * inv),
-                         pack_bf16x2(o_acc[8 * j + 6] * inv, o_acc[8 * j + 7] * inv));
-    }
-    __syncthreads();
-    {
+    if (softmax_role) asm volatile("bar.sync 3, %0;" ::"n"(ATC_THREADS) : "memory");   // (the accumulation warps' side is above)
+    __syncthreads();                                                                  // staged tile complete
+    {   // whole 256-byte row segments to global, all 12 warps
         __nv_bfloat16* O = a.o + b * a.o_batch_stride + h * 128;
         const long long ld = static_cast<long long>(a.H) * 128;
-#pragma unroll
-        for (int i = 0; i < (128 * 16) / ATC_THREADS; ++i) {
-            const int piece = threadIdx.x + i * ATC_THREADS;
+        for (int piece = threadIdx.x; piece < 128 * 16; piece += ATC_THREADS) {
             const int r = piece >> 4, pc = piece & 15;
             if (q0 + r < a.Sq) {
                 const uint4 u = ld_shared_v4(sQ + static_cast<uint32_t>(r) * ATC_O_PITCH + static_cast<uint32_t>(pc) * 16u);
