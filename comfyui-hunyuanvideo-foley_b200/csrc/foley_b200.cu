@@ -3,3 +3,4 @@
 #include "api.cu"
 #include "engine.cu"
 #include "dac.cu"
+#include "encoders.cu"

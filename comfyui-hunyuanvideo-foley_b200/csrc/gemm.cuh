@@ -39,7 +39,7 @@ enum EpiMode : int {
     EPI_F32 = 2,     // out(fp32)[split] = acc     (raw partial sums; consumer applies bias/gate)
     EPI_DAC = 3,     // fp32 conv epilogue: y = acc + bias (+resid); out = y; out2 = snake(y) / tanh(y)
 };
-enum ActMode : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU_TANH = 2, ACT_TANH = 3 };
+enum ActMode : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU_TANH = 2, ACT_TANH = 3, ACT_GELU_ERF = 4 };   // GELU_ERF: nn.GELU() of the CLAP text tower
 
 struct GemmEpi {
     int mode = EPI_BF16;
@@ -104,6 +104,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
         case ACT_SILU: return x / (1.0f + expf(-x));
         case ACT_GELU_TANH: return gelu_tanh_f(x);
         case ACT_TANH: return tanhf(x);
+        case ACT_GELU_ERF: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
         default: return x;
     }
 }
@@ -437,6 +438,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 } else if (e.act == ACT_GELU_TANH) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) a[j] = gelu_tanh_f(bf16_round(a[j]));
+                } else if (e.act == ACT_GELU_ERF) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { const float x = bf16_round(a[j]); a[j] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
                 } else if (e.act != ACT_NONE) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) a[j] = apply_act(bf16_round(a[j]), e.act);

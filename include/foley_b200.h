@@ -247,6 +247,57 @@ typedef struct foley_attn_args {
 } foley_attn_args;
 foley_status foley_attention(const foley_attn_args* args, void* stream);
 
+/* ---- condition encoders (feature_utils.py:64-79, 132-138; nodes.py:283-284) ----------------
+ * The reference moves its HF extractor modules to the device IN THE DiT's DTYPE before use, so these are the bf16
+ * modules: bf16 weights, fp32 accumulation, one bf16 rounding per op.  Weights are taken under their HF state-dict names
+ * ("vision_model.encoder.layers.3.self_attn.q_proj.weight", "text_model.encoder.layer.0.attention.self.query.weight",
+ * ...) from host tensors or straight from the model.safetensors of the HF snapshot; tensors of modules the path does
+ * not run (SigLIP text tower, CLAP pooler / projection) are accepted and ignored. */
+enum { FOLEY_ENC_SIGLIP_VISION = 0, FOLEY_ENC_CLAP_TEXT = 1 };
+typedef struct foley_encoder_config {
+    int32_t kind;                 /* FOLEY_ENC_* */
+    int32_t hidden_size;          /* 768 */
+    int32_t num_heads;            /* 12; head_dim must be 64 */
+    int32_t num_layers;           /* 12 */
+    int32_t intermediate_size;    /* 3072 */
+    float   layer_norm_eps;       /* 1e-6 (google/siglip2-base-patch16-512) / 1e-12 (laion/larger_clap_general text) */
+    int32_t image_size;           /* SigLIP: 512 */
+    int32_t patch_size;           /* SigLIP: 16 */
+    int32_t vocab_size;           /* CLAP: 50265 */
+    int32_t max_positions;        /* CLAP: 514 */
+    int32_t pad_token_id;         /* CLAP: 1 */
+    int32_t max_frames_per_pass;  /* SigLIP: frames encoded together (activation memory ~17 MB per frame); 0 = 48 */
+} foley_encoder_config;
+typedef struct foley_encoder foley_encoder;
+foley_status foley_encoder_create(const foley_encoder_config* cfg, int device, foley_encoder** out);
+void         foley_encoder_destroy(foley_encoder* e);
+foley_status foley_encoder_load_tensor(foley_encoder* e, const char* name, const void* data, const int64_t* shape,
+                                       int32_t ndim, int32_t dtype);
+foley_status foley_encoder_load_safetensors(foley_encoder* e, const char* path, const char* prefix, int64_t* n_loaded);
+foley_status foley_encoder_finalize(foley_encoder* e);
+/* encode_video_with_siglip2 (feature_utils.py:64-79): pixels = DEVICE fp32 [n_frames, 3, image, image] (the output of
+ * foley_preprocess_frames) -> out = DEVICE bf16 [n_frames, hidden]: `get_image_features(...).pooler_output`. */
+foley_status foley_siglip_encode(foley_encoder* e, const float* pixels, int32_t n_frames, void* out, void* stream);
+/* encode_text_feat (feature_utils.py:132-138): ids / mask = HOST int32 [batch, T] (tokenizer input_ids and
+ * attention_mask, padding=True; mask NULL = all ones) -> out = DEVICE bf16 [batch, T, hidden]: `last_hidden_state`,
+ * padded positions included exactly as the reference passes them on. */
+foley_status foley_clap_text_encode(foley_encoder* e, const int32_t* ids, const int32_t* mask, int32_t batch, int32_t T,
+                                    void* out, void* stream);
+/* "layers_run": stop after this many transformer layers (per-layer parity taps; -1 = all). */
+foley_status foley_encoder_set_option(foley_encoder* e, const char* key, int64_t value);
+int64_t      foley_encoder_launch_count(const foley_encoder* e);
+/* Activation buffers of the last call as HOST fp32: "x" residual stream, "h" last LayerNorm output, "qkv", "att", "y", "mlp". */
+foley_status foley_encoder_debug_read(foley_encoder* e, const char* what, float* dst, int64_t cap, int64_t* n_out);
+/* softmax(Q K^T * scale) V for head_dim 64 (HF SiglipAttention / ClapTextSelfAttention / nn.MultiheadAttention of the
+ * pooling head).  Element (b, h, r, d) of an operand at ptr + b*batch_stride + r*row_stride + h*64 + d (bf16, device).
+ * impl 0: flash-style kernel, no mask; impl 1: one warp per query row, key_mask = DEVICE int32 [batch, Sk] (0 = padded
+ * key) and optional bf16 rounding of scores and probabilities (the bmm + softmax path of nn.MultiheadAttention). */
+foley_status foley_attention_d64(const void* q, const void* k, const void* v, void* out, int32_t batch, int32_t heads,
+                                 int32_t Sq, int32_t Sk, int64_t q_batch_stride, int64_t q_row_stride,
+                                 int64_t kv_batch_stride, int64_t kv_row_stride, int64_t o_batch_stride,
+                                 int64_t o_row_stride, float scale, const int32_t* key_mask, int32_t round_scores,
+                                 int32_t impl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

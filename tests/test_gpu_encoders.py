@@ -1,0 +1,199 @@
+"""Condition encoders through the C ABI against the HF modules the reference runs
+(feature_utils.py:64-79 `siglip2_model.get_image_features(...).pooler_output`, :132-138 `clap_model(...).last_hidden_state`),
+instantiated from their configs with seeded random weights (no checkpoint is available offline) and moved to the device in
+bf16 exactly as the reference's Sampler does (nodes.py:283-284).
+
+Tolerance (floating point, stated here): the reference path is a bf16 module, so its own distance to the fp32 module is the
+floor.  Asserted: engine vs HF-fp32 <= 1.25 x (HF-bf16 vs HF-fp32) + 5e-4, and engine vs HF-bf16 <= 2 x that floor.  The
+head_dim-64 attention kernels alone: <= 4e-3 against fp32 softmax(QK^T/8)V on the same bf16 operands (P and the output are
+rounded to bf16, 2^-9 relative each)."""
+import pytest
+import torch
+
+from conftest import load_pkg, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _perturb(model, seed):
+    """HF's init leaves LayerNorm at (1, 0) and biases at 0: move every parameter so that each one matters."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() == 1 and ("norm" in name.lower()) and name.endswith("weight"):
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+            elif p.dim() == 1:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+            else:
+                p.add_(0.01 * torch.randn(p.shape, generator=g))
+    return model
+
+
+def _ref_attn64(q, k, v, H, mask=None):
+    B, Sq, Sk = q.shape[0], q.shape[1], k.shape[1]
+    qf = q.float().view(B, Sq, H, 64).transpose(1, 2)
+    kf = k.float().view(B, Sk, H, 64).transpose(1, 2)
+    vf = v.float().view(B, Sk, H, 64).transpose(1, 2)
+    s = qf @ kf.transpose(-1, -2) * 0.125
+    if mask is not None:
+        s = s.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
+    return (s.softmax(-1) @ vf).transpose(1, 2).reshape(B, Sq, H * 64)
+
+
+@pytest.mark.parametrize("name,B,H,Sq,Sk,impl", [
+    ("siglip_frame", 2, 12, 1024, 1024, 0), ("ragged", 2, 3, 130, 77, 0), ("one_tile", 1, 2, 64, 64, 0),
+    ("tiny", 1, 1, 5, 3, 0), ("clap", 2, 12, 77, 77, 1), ("clap_long", 1, 12, 300, 300, 1), ("pool", 3, 12, 1, 1024, 1)])
+def test_attention_d64_vs_fp32(name, B, H, Sq, Sk, impl):
+    enc = load_pkg("encoders")
+    g = torch.Generator(device="cuda").manual_seed(len(name) * 7 + Sq)
+    C = H * 64
+    if Sq == Sk:     # operands read in place from a fused projection output [B, S, 3C]
+        qkv = torch.randn(B, Sq, 3 * C, device="cuda", generator=g).bfloat16()
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    else:
+        q = torch.randn(B, Sq, C, device="cuda", generator=g).bfloat16()
+        kv = torch.randn(B, Sk, 2 * C, device="cuda", generator=g).bfloat16()
+        k, v = kv[..., :C], kv[..., C:]
+    mask = None
+    if impl == 1 and name.startswith("clap"):
+        mask = torch.ones(B, Sk, dtype=torch.int32, device="cuda")
+        mask[0, Sk - Sk // 3:] = 0
+    out = enc.attention_d64(q, k, v, H, key_mask=mask, impl=impl)
+    want = _ref_attn64(q, k, v, H, mask)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out.float(), want) < 4e-3, name
+
+
+def test_pool_attention_rounds_like_multihead_attention():
+    """nn.MultiheadAttention with need_weights (the SigLIP pooling head's call) rounds the bmm scores and the softmax to bf16."""
+    enc = load_pkg("encoders")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, H, Sk = 4, 12, 1024
+    C = H * 64
+    mha = torch.nn.MultiheadAttention(C, H, batch_first=True).cuda().bfloat16().eval()
+    probe = torch.randn(1, 1, C, device="cuda", generator=g).bfloat16()
+    xs = torch.randn(B, Sk, C, device="cuda", generator=g).bfloat16()
+    with torch.inference_mode():
+        Wq, Wk, Wv = mha.in_proj_weight.chunk(3)
+        bq, bk, bv = mha.in_proj_bias.chunk(3)
+        q = torch.nn.functional.linear(probe, Wq, bq).expand(B, 1, C).contiguous()
+        k = torch.nn.functional.linear(xs, Wk, bk)
+        v = torch.nn.functional.linear(xs, Wv, bv)
+        want = mha(probe.expand(B, 1, C), xs, xs)[0]
+        got = torch.nn.functional.linear(enc.attention_d64(q, k, v, H, round_scores=True, impl=1), mha.out_proj.weight, mha.out_proj.bias)
+    assert rel_l2(got.float(), want.float()) < 4e-3
+
+
+def _siglip(layers, image, seed):
+    from transformers import SiglipVisionConfig, SiglipVisionModel
+    cfg = SiglipVisionConfig(hidden_size=768, intermediate_size=3072, num_hidden_layers=layers, num_attention_heads=12,
+                             image_size=image, patch_size=16, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6)
+    torch.manual_seed(seed)
+    return _perturb(SiglipVisionModel(cfg).eval(), seed + 1)
+
+
+def _gate(got, ref_bf16, ref_fp32, what):
+    floor = rel_l2(ref_bf16.float(), ref_fp32)
+    d32, d16 = rel_l2(got.float(), ref_fp32), rel_l2(got.float(), ref_bf16.float())
+    print(f"{what}: engine vs fp32 {d32:.3e}, engine vs HF bf16 {d16:.3e}, HF bf16 vs fp32 (floor) {floor:.3e}")
+    assert torch.isfinite(got.float()).all()
+    assert d32 <= 1.25 * floor + 5e-4, (what, d32, floor)
+    assert d16 <= 2.0 * floor + 5e-4, (what, d16, floor)
+
+
+@pytest.mark.parametrize("layers,image,frames", [(2, 64, 5), (3, 512, 2), (12, 512, 3)])
+def test_siglip_vision_vs_hf(layers, image, frames):
+    enc = load_pkg("encoders")
+    model = _siglip(layers, image, 11 * layers)
+    g = torch.Generator().manual_seed(3)
+    px = (torch.rand(frames, 3, image, image, generator=g) * 2 - 1).cuda()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.inference_mode():
+        m32 = model.cuda().float()
+        ref32 = m32(pixel_values=px).pooler_output.float()
+        e = enc.SiglipVisionEncoder.from_hf(m32)
+        m16 = m32.to(torch.bfloat16)
+        ref16 = m16(pixel_values=px).pooler_output
+    got = e.encode(px)
+    torch.cuda.synchronize()
+    assert got.shape == (frames, 768) and got.dtype == torch.bfloat16
+    _gate(got, ref16, ref32, f"siglip L={layers} img={image}")
+    # frames are independent: a one-frame call reproduces its row bit for bit (same kernels, same tiles per frame)
+    one = e.encode(px[1:2])
+    assert torch.equal(one[0], got[1])
+
+
+def test_siglip_chunked_passes_match():
+    """max_frames_per_pass only bounds activation memory: the result does not depend on it."""
+    enc = load_pkg("encoders")
+    model = _siglip(2, 64, 4)
+    px = (torch.rand(7, 3, 64, 64, generator=torch.Generator().manual_seed(9)) * 2 - 1).cuda()
+    cfg = dict(enc.SIGLIP2_BASE_512, num_layers=2, image_size=64)
+    a = enc.SiglipVisionEncoder(cfg).load_state_dict(model.state_dict()).finalize()
+    b = enc.SiglipVisionEncoder(cfg, max_frames_per_pass=3).load_state_dict(model.state_dict()).finalize()
+    assert torch.equal(a.encode(px), b.encode(px))
+
+
+def test_siglip_layer_taps_vs_hf():
+    """Residual stream after every layer (option layers_run) against HF's hidden_states, bf16 module vs fp32 module."""
+    enc = load_pkg("encoders")
+    model = _siglip(4, 64, 21)
+    px = (torch.rand(3, 3, 64, 64, generator=torch.Generator().manual_seed(2)) * 2 - 1).cuda()
+    with torch.inference_mode():
+        m32 = model.cuda().float()
+        hs32 = m32(pixel_values=px, output_hidden_states=True).hidden_states
+        e = enc.SiglipVisionEncoder.from_hf(m32)
+        hs16 = m32.to(torch.bfloat16)(pixel_values=px, output_hidden_states=True).hidden_states
+    n = 3 * 16 * 768
+    for i in range(5):
+        e.set_option("layers_run", i)
+        e.encode(px)
+        x = e.debug_read("x", n).view(3, 16, 768)
+        _gate(x, hs16[i].cpu(), hs32[i].float().cpu(), f"siglip residual stream after {i} layers")
+
+
+def _clap(layers, seed):
+    from transformers import ClapTextConfig, ClapTextModelWithProjection
+    cfg = ClapTextConfig(num_hidden_layers=layers)
+    torch.manual_seed(seed)
+    return _perturb(ClapTextModelWithProjection(cfg).eval(), seed + 1)
+
+
+@pytest.mark.parametrize("layers,T", [(2, 9), (12, 24), (12, 77)])
+def test_clap_text_vs_hf(layers, T):
+    enc = load_pkg("encoders")
+    model = _clap(layers, 5 + layers)
+    g = torch.Generator().manual_seed(T)
+    ids = torch.randint(3, 50265, (2, T), generator=g)
+    ids[:, 0] = 0
+    n0 = max(3, T // 2)                     # the negative prompt is shorter: right-padded with pad_token_id = 1
+    ids[0, n0 - 1] = 2
+    ids[0, n0:] = 1
+    ids[1, T - 1] = 2
+    mask = (ids != 1).long()
+    with torch.inference_mode():
+        m32 = model.cuda().float()
+        ref32 = m32(input_ids=ids.cuda(), attention_mask=mask.cuda(), output_hidden_states=True).last_hidden_state.float()
+        e = enc.ClapTextEncoder.from_hf(m32)
+        ref16 = m32.to(torch.bfloat16)(input_ids=ids.cuda(), attention_mask=mask.cuda(), output_hidden_states=True).last_hidden_state
+    got = e.encode(ids, mask)
+    torch.cuda.synchronize()
+    assert got.shape == (2, T, 768)
+    _gate(got, ref16, ref32, f"clap L={layers} T={T}")
+    # the rows the reference hands on (padded positions included) are all there and finite
+    assert torch.isfinite(got[0, n0:].float()).all()
+
+
+def test_encoder_errors():
+    enc = load_pkg("encoders")
+    E = load_pkg("engine")
+    with pytest.raises(E.FoleyError):
+        enc.SiglipVisionEncoder(dict(enc.SIGLIP2_BASE_512, num_heads=8))          # head_dim 96
+    e = enc.SiglipVisionEncoder(dict(enc.SIGLIP2_BASE_512, num_layers=1, image_size=64))
+    with pytest.raises(E.FoleyError, match="missing tensor"):
+        e.finalize()
+    c = enc.ClapTextEncoder(dict(enc.CLAP_TEXT_GENERAL, num_layers=1))
+    with pytest.raises(E.FoleyError):
+        c.encode(torch.zeros(1, 4, dtype=torch.long))                              # not finalized: weights missing
