@@ -57,6 +57,11 @@ def _lib():
     return lib
 
 
+class _Cfg(dict):
+    """dict with attribute access: `deps.clap_model.config.max_position_embeddings` (reference utils.py:97-101 `_caps`)."""
+    __getattr__ = dict.get
+
+
 class _Encoder:
     KIND = None
     DEFAULTS = {}
@@ -69,7 +74,9 @@ class _Encoder:
         c = dict(self.DEFAULTS)
         c.update(config or {})
         c.update(overrides)
-        self.config = c
+        self.config = _Cfg(c)
+        if "max_positions" in c:
+            self.config["max_position_embeddings"] = c["max_positions"]
         self.cfg = _EncConfig(kind=self.KIND, **{k: v for k, v in c.items() if k in dict(_EncConfig._fields_)})
         self._h = c_void_p()
         _check(self.lib.foley_encoder_create(ctypes.byref(self.cfg), self.device.index or 0, ctypes.byref(self._h)))

@@ -197,3 +197,64 @@ def test_encoder_errors():
     c = enc.ClapTextEncoder(dict(enc.CLAP_TEXT_GENERAL, num_layers=1))
     with pytest.raises(E.FoleyError):
         c.encode(torch.zeros(1, 4, dtype=torch.long))                              # not finalized: weights missing
+
+
+class _FakeTokenizer:
+    """Stands in for HF's tokenizer (no vocabulary files offline): deterministic ids, right padding with pad id 1."""
+    model_max_length = 512
+
+    def __call__(self, texts, padding=True, return_tensors="pt"):
+        rows = [[0] + [3 + (ord(c) * 31 + i) % 50000 for i, c in enumerate(t)][:60] + [2] for t in texts]
+        T = max(len(r) for r in rows)
+        ids = torch.tensor([r + [1] * (T - len(r)) for r in rows])
+        return {"input_ids": ids, "attention_mask": (ids != 1).long()}
+
+
+def test_sampler_runs_frames_to_waveform_on_the_engine_encoders():
+    """Frames -> GPU preprocessing -> SigLIP2 on the engine + CLAP text on the engine (+ a stub for the borrowed Synchformer)
+    -> denoise -> DAC through HunyuanFoleySampler.generate_audio; the features the Sampler consumed equal the HF modules'
+    on the same preprocessed frames / token ids within the bf16 floor."""
+    nodes, cfgmod, E, enc, fb = (load_pkg(m) for m in ("nodes", "config", "engine", "encoders", "feature_bridge"))
+    from oracle import weights as W
+    c = W.model_config("tiny")
+    sd = W.synth_dit_state_dict(c, seed=0)
+    cfg = cfgmod.load_model_config("xxl")
+    for k in ("hidden_size", "num_heads", "depth_triple_blocks", "depth_single_blocks"):
+        cfg.model_config.model_kwargs[k] = c[k]
+    eng = E.FoleyEngine(dict(cfg.model_config.model_kwargs))
+    eng.load_state_dict(sd)
+    eng.finalize()
+    model = nodes.FoleyModel(eng, sd["empty_clip_feat"], sd["empty_sync_feat"], cfg, dtype=torch.bfloat16)
+    dac = nodes.FoleyDAC.from_state_dict(W.synth_dac_state_dict(W.DAC_TINY, seed=3))
+    hf_sig, hf_clap = _siglip(2, 512, 31).cuda(), _clap(2, 32).cuda()
+    sig = enc.SiglipVisionEncoder.from_hf(hf_sig)
+    clap = enc.ClapTextEncoder.from_hf(hf_clap)
+    L, Lv, S = W.clip_lengths(1.0)
+    seen = {}
+
+    def sync_encode(frames):
+        seen["sync_in"] = frames
+        return W.synth_conditions(c, L, Lv, S)["syncformer_feat"].cuda()
+
+    inner = fb.make_extract_features(sig, _FakeTokenizer(), clap, sync_encode, torch.device("cuda"))
+
+    def extract(pre8, pre25, prompt, negative_prompt):
+        out = inner(pre8, pre25, prompt, negative_prompt)
+        seen["pre8"], seen["out"] = pre8, out
+        return out
+
+    deps = cfgmod.AttributeDict({"dac_model": dac, "extract_features": extract, "preprocessed_inputs": True,
+                                 "clap_tokenizer": _FakeTokenizer(), "clap_model": clap})
+    image = torch.rand(8, 48, 64, 3, generator=torch.Generator().manual_seed(4))
+    first, batch = nodes.HunyuanFoleySampler().generate_audio(model, deps, 8.0, 1.0, "rain on a tin roof", "noisy", 4.5, 4,
+                                                              "euler", 1, 0, True, image=image)
+    assert batch["waveform"].shape == (1, 1, 48000) and torch.isfinite(batch["waveform"]).all()
+    visual, text, audio_len = seen["out"]
+    assert visual["siglip2_feat"].shape == (1, 8, 768) and seen["sync_in"].shape == (1, 25, 3, 224, 224) and audio_len == 1.0
+    tok = _FakeTokenizer()(["noisy", "rain on a tin roof"])
+    assert text["uncond_text_feat"].shape == (1, tok["input_ids"].shape[1], 768) and text["text_feat"].shape == text["uncond_text_feat"].shape
+    with torch.inference_mode():
+        want_sig = hf_sig.to(torch.bfloat16)(pixel_values=seen["pre8"]).pooler_output
+        want_txt = hf_clap.to(torch.bfloat16)(input_ids=tok["input_ids"].cuda(), attention_mask=tok["attention_mask"].cuda()).last_hidden_state
+    assert rel_l2(visual["siglip2_feat"][0].float(), want_sig.float()) < 2e-2
+    assert rel_l2(torch.cat([text["uncond_text_feat"], text["text_feat"]]).float(), want_txt.float()) < 2e-2

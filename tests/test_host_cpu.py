@@ -481,3 +481,43 @@ def test_precision_other_than_bf16_is_refused_not_substituted(monkeypatch):
     monkeypatch.setenv("FOLEY_B200_PRECISION_FALLBACK", "bf16")
     nodes._check_precision("fp32")
     nodes._check_precision("auto", torch.float16)
+
+
+def test_feature_bridge_wires_encoders_like_the_reference():
+    """Host logic of feature_bridge.make_extract_features with fake encoders: prompts are tokenised as [negative, prompt]
+    with padding (feature_utils.py:134, utils.py:284), row 0 becomes uncond_text_feat and row 1 text_feat
+    (utils.py:286), SigLIP features get the leading batch axis (feature_utils.py:77-78), the audio length follows the
+    25 fps stream (utils.py:281), and a missing Synchformer only blocks video-to-audio."""
+    fb, E = load_pkg("feature_bridge"), load_pkg("engine")
+    calls = {}
+
+    class Tok:
+        def __call__(self, texts, padding=True, return_tensors="pt"):
+            calls["texts"], calls["padding"] = list(texts), padding
+            ids = torch.tensor([[0, 5, 2, 1, 1], [0, 7, 8, 9, 2]])
+            return {"input_ids": ids, "attention_mask": (ids != 1).long()}
+
+    class Sig:
+        def encode(self, px):
+            return torch.full((px.shape[0], 768), 2.0)
+
+    class Clap:
+        def encode(self, ids, mask):
+            calls["mask"] = mask
+            return torch.arange(2.0).view(2, 1, 1).expand(2, ids.shape[1], 768)
+
+    dev = torch.device("cpu")
+    ex = fb.make_extract_features(Sig(), Tok(), Clap(), lambda fr: torch.zeros(1, 8 * ((fr.shape[1] - 16) // 8 + 1), 768), dev)
+    visual, text, alen = ex(torch.zeros(8, 3, 512, 512), torch.zeros(25, 3, 224, 224), "a dog barks", "noisy")
+    assert calls["texts"] == ["noisy", "a dog barks"] and calls["padding"] is True
+    assert visual["siglip2_feat"].shape == (1, 8, 768) and visual["syncformer_feat"].shape == (1, 16, 768) and alen == 1.0
+    assert float(text["uncond_text_feat"].max()) == 0.0 and float(text["text_feat"].min()) == 1.0
+    assert text["text_feat"].shape == (1, 5, 768) and calls["mask"].tolist() == [[1, 1, 1, 0, 0], [1, 1, 1, 1, 1]]
+    # text-to-audio needs no visual encoder at all
+    ex_t2a = fb.make_extract_features(Sig(), Tok(), Clap(), "reference package not installed", dev)
+    visual, text, alen = ex_t2a(None, None, "p", "n")
+    assert visual == {} and alen is None and text["text_feat"].shape == (1, 5, 768)
+    with pytest.raises(E.FoleyError, match="Synchformer"):
+        ex_t2a(torch.zeros(8, 3, 512, 512), torch.zeros(25, 3, 224, 224), "p", "n")
+    with pytest.raises(E.FoleyError, match="tokens"):
+        fb.make_extract_features(Sig(), Tok(), Clap(), "x", dev, max_text_tokens=4)(None, None, "p", "n")
