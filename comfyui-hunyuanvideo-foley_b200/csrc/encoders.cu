@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "attention_tc64.cuh"
 #include "encoders.cuh"
 #include "engine.cuh"
 #include "gemm_host.cuh"
@@ -37,6 +38,8 @@ class Encoder {
     int device = 0, num_sms = 148;
     int C = 0, H = 0, NL = 0, F = 0;
     bool finalized = false;
+    int att_tc = 1;                        // self-attention of the vision tower: 1 = tcgen05 / TMEM kernel (attention_tc64.cuh), 0 = the
+                                           // mma.sync flash kernel (FOLEY_ENC_ATT_TC=0; option "att_tc")
     int layers_run = -1;                   // option "layers_run": stop after this many layers (per-layer parity taps); -1 = all
     int64_t launches = 0;
     std::unordered_map<std::string, RawTensor> raw;
@@ -133,6 +136,8 @@ foley_status Encoder::create(const foley_encoder_config* c, int dev) {
     if (!gemm_init_attributes(&err)) return fail(FOLEY_ERR_CUDA, err);
     FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
     FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    FOLEY_CUDA_OK(attention_tc64_init());
+    if (const char* e = getenv("FOLEY_ENC_ATT_TC")) att_tc = atoi(e);
     layers.resize(NL);
     return FOLEY_OK;
 }
@@ -371,6 +376,13 @@ foley_status Encoder::attention(cudaStream_t st, const EncAttnArgs& a, bool smal
         if (smem > 64 * 1024) return fail(FOLEY_ERR_UNSUPPORTED, "small attention: too many keys");
         const long long units = static_cast<long long>(a.B) * a.H * a.Sq;
         FOLEY_CUDA_OK(launch_k(enc_small_attention_kernel, dim3(enc_blocks(units, ESA_WARPS)), dim3(32 * ESA_WARPS), smem, st, a));
+    } else if (att_tc) {
+        AttTc64Args t;
+        t.o = a.o; t.o_batch_stride = a.o_batch_stride; t.o_row_stride = a.o_row_stride; t.H = a.H; t.Sq = a.Sq; t.Sk = a.Sk;
+        t.scale_log2 = a.scale * 1.4426950408889634f;
+        std::string err;
+        if (!launch_attention_tc64(a.q, a.k, a.v, a.q_row_stride, a.q_batch_stride, a.kv_row_stride, a.kv_batch_stride, a.B, t, st, &err))
+            return fail(FOLEY_ERR_CUDA, err);
     } else {
         dim3 grid((a.Sq + EA_BM - 1) / EA_BM, a.H, a.B);
         FOLEY_CUDA_OK(launch_k(enc_attention_kernel, grid, dim3(32 * EA_NW), EA_SMEM, st, a));
@@ -604,6 +616,7 @@ extern "C" foley_status foley_encoder_set_option(foley_encoder* e, const char* k
     if (!e || !key) return fail(FOLEY_ERR_INVALID, "foley_encoder_set_option: null argument");
     const std::string k(key);
     if (k == "layers_run") { e->impl.layers_run = static_cast<int>(value); return FOLEY_OK; }
+    if (k == "att_tc") { e->impl.att_tc = static_cast<int>(value); return FOLEY_OK; }
     return fail(FOLEY_ERR_INVALID, "unknown encoder option " + k);
 }
 extern "C" int64_t foley_encoder_launch_count(const foley_encoder* e) { return e ? e->impl.launches : 0; }
@@ -615,14 +628,14 @@ extern "C" foley_status foley_encoder_debug_read(foley_encoder* e, const char* w
 }
 
 // softmax(Q K^T * scale) V for head_dim 64, exported for unit tests.  impl 0: flash kernel (no mask); impl 1: one warp per
-// query row (key mask, optional bf16 rounding of scores).
+// query row (key mask, optional bf16 rounding of scores); impl 2: tcgen05 / TMEM kernel (no mask).
 extern "C" foley_status foley_attention_d64(const void* q, const void* k, const void* v, void* out, int32_t batch, int32_t heads,
                                             int32_t Sq, int32_t Sk, int64_t q_batch_stride, int64_t q_row_stride,
                                             int64_t kv_batch_stride, int64_t kv_row_stride, int64_t o_batch_stride,
                                             int64_t o_row_stride, float scale, const int32_t* key_mask, int32_t round_scores,
                                             int32_t impl, void* stream) {
     if (!q || !k || !v || !out || batch < 1 || heads < 1 || Sq < 1 || Sk < 1) return fail(FOLEY_ERR_INVALID, "foley_attention_d64: bad argument");
-    if (impl == 0 && (key_mask || round_scores)) return fail(FOLEY_ERR_UNSUPPORTED, "foley_attention_d64: the flash kernel takes no mask");
+    if (impl != 1 && (key_mask || round_scores)) return fail(FOLEY_ERR_UNSUPPORTED, "foley_attention_d64: the flash kernels take no mask");
     EncAttnArgs a;
     a.q = static_cast<const bf16*>(q); a.k = static_cast<const bf16*>(k); a.v = static_cast<const bf16*>(v); a.o = static_cast<bf16*>(out);
     a.B = batch; a.H = heads; a.Sq = Sq; a.Sk = Sk;
@@ -633,7 +646,17 @@ extern "C" foley_status foley_attention_d64(const void* q, const void* k, const 
     if (!attr) {
         FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
         FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        FOLEY_CUDA_OK(attention_tc64_init());
         attr = true;
+    }
+    if (impl == 2) {
+        AttTc64Args t;
+        t.o = a.o; t.o_batch_stride = o_batch_stride; t.o_row_stride = o_row_stride; t.H = heads; t.Sq = Sq; t.Sk = Sk;
+        t.scale_log2 = scale * 1.4426950408889634f;
+        std::string err;
+        if (!launch_attention_tc64(a.q, a.k, a.v, q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride, batch, t, st, &err))
+            return fail(FOLEY_ERR_CUDA, err);
+        return FOLEY_OK;
     }
     if (impl == 1) {
         const size_t smem = static_cast<size_t>(ESA_WARPS) * Sk * sizeof(float);

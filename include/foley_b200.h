@@ -283,14 +283,15 @@ foley_status foley_siglip_encode(foley_encoder* e, const float* pixels, int32_t 
  * padded positions included exactly as the reference passes them on. */
 foley_status foley_clap_text_encode(foley_encoder* e, const int32_t* ids, const int32_t* mask, int32_t batch, int32_t T,
                                     void* out, void* stream);
-/* "layers_run": stop after this many transformer layers (per-layer parity taps; -1 = all). */
+/* "layers_run": stop after this many transformer layers (per-layer parity taps; -1 = all); "att_tc": 1 = tcgen05 / TMEM
+ * self-attention kernel in the vision tower (default), 0 = the mma.sync flash kernel. */
 foley_status foley_encoder_set_option(foley_encoder* e, const char* key, int64_t value);
 int64_t      foley_encoder_launch_count(const foley_encoder* e);
 /* Activation buffers of the last call as HOST fp32: "x" residual stream, "h" last LayerNorm output, "qkv", "att", "y", "mlp". */
 foley_status foley_encoder_debug_read(foley_encoder* e, const char* what, float* dst, int64_t cap, int64_t* n_out);
 /* softmax(Q K^T * scale) V for head_dim 64 (HF SiglipAttention / ClapTextSelfAttention / nn.MultiheadAttention of the
  * pooling head).  Element (b, h, r, d) of an operand at ptr + b*batch_stride + r*row_stride + h*64 + d (bf16, device).
- * impl 0: flash-style kernel, no mask; impl 1: one warp per query row, key_mask = DEVICE int32 [batch, Sk] (0 = padded
+ * impl 0: flash-style mma.sync kernel, no mask; impl 2: tcgen05 / TMEM kernel, no mask (the vision tower's default); impl 1: one warp per query row, key_mask = DEVICE int32 [batch, Sk] (0 = padded
  * key) and optional bf16 rounding of scores and probabilities (the bmm + softmax path of nn.MultiheadAttention). */
 foley_status foley_attention_d64(const void* q, const void* k, const void* v, void* out, int32_t batch, int32_t heads,
                                  int32_t Sq, int32_t Sk, int64_t q_batch_stride, int64_t q_row_stride,

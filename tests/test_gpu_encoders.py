@@ -42,7 +42,8 @@ def _ref_attn64(q, k, v, H, mask=None):
 
 @pytest.mark.parametrize("name,B,H,Sq,Sk,impl", [
     ("siglip_frame", 2, 12, 1024, 1024, 0), ("ragged", 2, 3, 130, 77, 0), ("one_tile", 1, 2, 64, 64, 0),
-    ("tiny", 1, 1, 5, 3, 0), ("clap", 2, 12, 77, 77, 1), ("clap_long", 1, 12, 300, 300, 1), ("pool", 3, 12, 1, 1024, 1)])
+    ("tiny", 1, 1, 5, 3, 0), ("tc_siglip_frame", 2, 12, 1024, 1024, 2), ("tc_ragged", 2, 3, 130, 77, 2), ("tc_one_chunk", 1, 2, 128, 128, 2),
+    ("tc_tiny", 1, 1, 5, 3, 0 + 2), ("tc_odd_chunks", 1, 2, 300, 333, 2), ("tc_many_ctas", 5, 12, 1024, 1024, 2), ("clap", 2, 12, 77, 77, 1), ("clap_long", 1, 12, 300, 300, 1), ("pool", 3, 12, 1, 1024, 1)])
 def test_attention_d64_vs_fp32(name, B, H, Sq, Sk, impl):
     enc = load_pkg("encoders")
     g = torch.Generator(device="cuda").manual_seed(len(name) * 7 + Sq)
@@ -63,6 +64,15 @@ def test_attention_d64_vs_fp32(name, B, H, Sq, Sk, impl):
     torch.cuda.synchronize()
     assert torch.isfinite(out.float()).all()
     assert rel_l2(out.float(), want) < 4e-3, name
+    assert load_pkg("engine").load_library() and all(f == 0 for f in _flags()), "a pipeline wait of the kernel timed out"
+
+
+def _flags():
+    import ctypes
+    lib = load_pkg("engine").load_library()
+    buf = (ctypes.c_uint32 * 4)()
+    lib.foley_debug_flags(buf)
+    return list(buf)
 
 
 def test_pool_attention_rounds_like_multihead_attention():
@@ -123,6 +133,11 @@ def test_siglip_vision_vs_hf(layers, image, frames):
     # frames are independent: a one-frame call reproduces its row bit for bit (same kernels, same tiles per frame)
     one = e.encode(px[1:2])
     assert torch.equal(one[0], got[1])
+    # the mma.sync attention kernel (option att_tc = 0) gives the same features within the attention kernels' own tolerance
+    e.set_option("att_tc", 0)
+    alt = e.encode(px)
+    assert rel_l2(alt.float(), got.float()) < 1.5e-2
+    _gate(alt, ref16, ref32, f"siglip L={layers} img={image} (mma.sync attention)")
 
 
 def test_siglip_chunked_passes_match():
