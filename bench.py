@@ -400,6 +400,9 @@ def run_b200(args):
                 if rank == 0:
                     extra[tag] = r
 
+        # ================= informational: the condition encoders of the same clip =================
+        enc_info = condition_encoders(args, dev) if rank == 0 and world == 1 and not args.no_encoders else None
+
         # ================= informational: the reference itself on this GPU, eager under CUDA autocast =================
         ref_gpu = None
         if rank == 0 and world == 1 and not args.no_ref_gpu:
@@ -435,6 +438,8 @@ def run_b200(args):
             line["parity"] = parity
         if ref_gpu is not None:
             line["reference_gpu_eager"] = ref_gpu
+        if enc_info is not None:
+            line["encoders"] = enc_info
         if extra:
             line["extra_configs"] = extra
         if world == 1 and not args.no_cpu_baseline:
@@ -566,6 +571,60 @@ def measure_config(model_name, B, duration, args, dev, world, rank, eng, E, node
     return out
 
 
+def condition_encoders(args, dev):
+    """Informational: SigLIP2 vision tower (+ pooling head) on the clip's 8 fps frames and the CLAP text tower on the prompt
+    pair, on the engine (encoders.py) and as the HF modules the reference runs (eager, bf16 module: nodes.py:283-284) on the
+    same GPU with the same seeded weights.  CUDA events after warm-up."""
+    try:
+        from transformers import ClapTextConfig, ClapTextModelWithProjection, SiglipVisionConfig, SiglipVisionModel
+        enc = load_pkg("encoders")
+
+        def timed(fn, iters=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / iters
+
+        torch.manual_seed(0)
+        T = int(args.duration * 8)
+        px = torch.rand(T, 3, 512, 512, device=dev) * 2 - 1
+        ids = torch.randint(3, 50265, (2, 77))
+        ids[:, 0] = 0
+        ids[0, 40:] = 1
+        mask = (ids != 1).long()
+        out = {}
+        with torch.inference_mode():
+            sig = SiglipVisionModel(SiglipVisionConfig(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
+                                                       image_size=512, patch_size=16, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6)).eval().to(dev)
+            e_sig = enc.SiglipVisionEncoder.from_hf(sig, device=dev)
+            sig = sig.to(torch.bfloat16)
+            got, want = e_sig.encode(px).float(), sig(pixel_values=px).pooler_output.float()
+            out["siglip2_vision"] = {"frames": T, "ms": timed(lambda: e_sig.encode(px)), "ms_hf_eager_bf16": timed(lambda: sig(pixel_values=px).pooler_output, 3),
+                                     "rel_l2_vs_hf_bf16": float((got - want).norm() / want.norm())}
+            del sig, e_sig
+            clap = ClapTextModelWithProjection(ClapTextConfig()).eval().to(dev)
+            e_clap = enc.ClapTextEncoder.from_hf(clap, device=dev)
+            clap = clap.to(torch.bfloat16)
+            idc, mc = ids.to(dev), mask.to(dev)
+            got, want = e_clap.encode(ids, mask).float(), clap(input_ids=idc, attention_mask=mc).last_hidden_state.float()
+            out["clap_text"] = {"tokens": [2, 77], "ms": timed(lambda: e_clap.encode(ids, mask)),
+                                "ms_hf_eager_bf16": timed(lambda: clap(input_ids=idc, attention_mask=mc).last_hidden_state),
+                                "rel_l2_vs_hf_bf16": float((got - want).norm() / want.norm())}
+            del clap, e_clap
+        torch.cuda.empty_cache()
+        out["what"] = ("SigLIP2-base-patch16-512 vision tower + pooling head and CLAP text tower (seeded random weights) on the engine vs the HF "
+                       "modules in bf16, eager, same GPU; Synchformer is not built (DESIGN.md §8)")
+        return out
+    except Exception as e:   # noqa: BLE001
+        return {"unavailable": repr(e)}
+
+
 def reference_gpu_eager(args, c, dev):
     """Informational: the UNMODIFIED reference on this GPU — bf16 weights, eager, torch.autocast("cuda", bf16) —
     ms per Euler step of its own denoise loop, CUDA events.  None when no reference tree is staged."""
@@ -654,6 +713,7 @@ def main():
     ap.add_argument("--denoise-steps", type=int, default=50)
     ap.add_argument("--cfg", type=float, default=4.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-encoders", action="store_true", help="skip the informational condition-encoder timing")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the informational eager-reference-on-GPU timing")
     ap.add_argument("--extra-configs", type=int, default=1, help="also time BASELINE.json configs 4 and 5 at their per-GPU shapes")
     ap.add_argument("--ref-steps", type=int, default=1, help="--impl reference: complete Euler steps timed per bench step")

@@ -335,11 +335,27 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
 }
 
 // ----------------------------------------------------------------------------- misc math
+#ifndef FOLEY_BF16_INT_ROUND
+#define FOLEY_BF16_INT_ROUND 0   // 1: round to bf16 with integer arithmetic (ALU pipe) instead of cvt.rn.bf16 (conversion unit)
+#endif
+#if FOLEY_BF16_INT_ROUND
+// Round-to-nearest-even to bf16 precision on the integer ALU: bit-identical to cvt.rn.bf16.f32 for every non-NaN input
+// (the carry out of the mantissa rounds up into the exponent, up to inf).
+__device__ __forceinline__ uint32_t bf16_round_bits(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return (u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u;
+}
+__device__ __forceinline__ float bf16_round(float x) { return __uint_as_float(bf16_round_bits(x)); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    return __byte_perm(bf16_round_bits(lo), bf16_round_bits(hi), 0x7632);
+}
+#else
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+#endif
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_tanh_f(float x) {
     // tanh(u) = 1 - 2 / (1 + e^{2u}) on the fast exp / divide units (abs error ~1e-6, far below the bf16 rounding
