@@ -31,11 +31,13 @@ extern "C" foley_status foley_gemm(const void* a, int32_t dtype, int64_t batch, 
                                    int64_t ldo, int64_t out_batch_stride, int64_t split_stride,
                                    void* stream) {
     if (!a || !w || !out) return fail(FOLEY_ERR_INVALID, "foley_gemm: null pointer");
-    if (dtype != FOLEY_DT_BF16 && dtype != FOLEY_DT_F32) return fail(FOLEY_ERR_INVALID, "foley_gemm: dtype");
+    if (dtype != FOLEY_DT_BF16 && dtype != FOLEY_DT_F32 && dtype != FOLEY_DT_F16) return fail(FOLEY_ERR_INVALID, "foley_gemm: dtype");
+    if (dtype == FOLEY_DT_F16 && mode != 0) return fail(FOLEY_ERR_UNSUPPORTED, "foley_gemm: fp16 operands exist for mode 0 (16-bit output) only");
     if (mode < 0 || mode > 2) return fail(FOLEY_ERR_INVALID, "foley_gemm: mode must be 0,1,2");
     GemmLaunch L;
     L.a.ptr = a;
-    L.a.dtype = dtype == FOLEY_DT_BF16 ? DT_BF16 : DT_F32;
+    L.a.dtype = dtype == FOLEY_DT_F32 ? DT_F32 : DT_BF16;     // fp16 shares the 16-bit operand layout and tensor maps
+    L.epi.f16 = dtype == FOLEY_DT_F16 ? 1 : 0;
     L.a.k = k; L.a.rows = rows; L.a.batch = batch; L.a.ld = lda; L.a.batch_stride = a_batch_stride;
     L.w = w; L.n = n;
     L.taps = taps; L.tap_off0 = tap_off0; L.tap_stride = tap_stride;

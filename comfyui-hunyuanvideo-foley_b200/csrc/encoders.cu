@@ -51,6 +51,16 @@ class Encoder {
     bf16 *probe = nullptr, *probe_q = nullptr;
     // CLAP
     bf16 *word = nullptr, *pos_tab = nullptr, *type_tab = nullptr, *emb_ln_w = nullptr, *emb_ln_b = nullptr;
+    // Synchformer (MotionFormer visual extractor): Linear weights hold IEEE fp16 bits (the module runs under fp16 autocast)
+    struct SyncBlockW {
+        LinearW qkv_t, proj_t, qkv_s, proj_s, fc1, fc2;
+        bf16 *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr, *n3w = nullptr, *n3b = nullptr;
+    };
+    std::vector<SyncBlockW> sblocks;
+    LinearW s_patch, s_in_proj, s_out_proj, s_lin1, s_lin2;
+    bf16 *s_norm_w = nullptr, *s_norm_b = nullptr, *s_an1w = nullptr, *s_an1b = nullptr, *s_an2w = nullptr, *s_an2b = nullptr;
+    float *s_tok_tab = nullptr, *s_agg_cls = nullptr;
+    float *xf = nullptr, *xn = nullptr;    // fp32 residual stream / normalised tokens (Synchformer only)
     // activations (grown on demand)
     long long cap_rows = 0;
     bf16 *x = nullptr, *h = nullptr, *qkv = nullptr, *att = nullptr, *y = nullptr, *mlp = nullptr;
@@ -65,6 +75,7 @@ class Encoder {
     foley_status finalize();
     foley_status siglip_encode(const float* pixels, int n_frames, void* out, cudaStream_t st);
     foley_status clap_encode(const int32_t* ids, const int32_t* mask, int B, int T, void* out, cudaStream_t st);
+    foley_status synchformer_encode(const float* frames, int n_frames, float* out, cudaStream_t st);
     foley_status debug_read(const char* what, float* dst, int64_t cap, int64_t* n_out);
     cudaStream_t pick_stream(void* st) { return st ? static_cast<cudaStream_t>(st) : own_stream; }
     foley_status order_after(void* caller_stream) {   // legacy-stream callers: see Engine::order_after
@@ -82,7 +93,10 @@ class Encoder {
     foley_status take_rows(const std::string& wname, const std::string& bname, int row0, int rows, int k, LinearW* out);
     foley_status take_qkv(const std::string& q, const std::string& k, const std::string& v, LinearW* out);
     foley_status ensure_rows(long long rows);
-    foley_status gemm(cudaStream_t st, const bf16* A, long long rows, const LinearW& W, bf16* out, int act);
+    foley_status gemm(cudaStream_t st, const bf16* A, long long rows, const LinearW& W, bf16* out, int act, int f16 = 0);
+    foley_status take_linear_f16(const std::string& name, LinearW* out, int n_expected, int k_expected);
+    foley_status take_rows_f16(const std::string& wname, const std::string& bname, int n, int k, LinearW* out);
+    foley_status sync_ln(cudaStream_t st, SyncLnArgs a);
     foley_status add_ln(cudaStream_t st, EncLnArgs a);
     foley_status attention(cudaStream_t st, const EncAttnArgs& a, bool small);
     void free_all();
@@ -100,6 +114,8 @@ void Encoder::free_all() {
         if (*p) { cudaFree(*p); *p = nullptr; }
     for (int** p : {&ids_dev, &pos_dev, &mask_dev})
         if (*p) { cudaFree(*p); *p = nullptr; }
+    for (float** p : {&xf, &xn})
+        if (*p) { cudaFree(*p); *p = nullptr; }
     cap_rows = 0;
 }
 
@@ -114,7 +130,8 @@ foley_status Encoder::create(const foley_encoder_config* c, int dev) {
     cfg = *c;
     device = dev;
     C = cfg.hidden_size; H = cfg.num_heads; NL = cfg.num_layers; F = cfg.intermediate_size;
-    if (cfg.kind != FOLEY_ENC_SIGLIP_VISION && cfg.kind != FOLEY_ENC_CLAP_TEXT) return fail(FOLEY_ERR_INVALID, "encoder kind");
+    if (cfg.kind != FOLEY_ENC_SIGLIP_VISION && cfg.kind != FOLEY_ENC_CLAP_TEXT && cfg.kind != FOLEY_ENC_SYNCHFORMER)
+        return fail(FOLEY_ERR_INVALID, "encoder kind");
     if (C != 768) return fail(FOLEY_ERR_UNSUPPORTED, "encoder hidden_size must be 768 (SigLIP2-base / CLAP text)");
     if (H <= 0 || C / H != 64 || C % H != 0) return fail(FOLEY_ERR_UNSUPPORTED, "encoder head_dim must be 64");
     if (NL < 1 || F < 64 || F % 64 != 0) return fail(FOLEY_ERR_INVALID, "encoder depth / intermediate size");
@@ -122,6 +139,9 @@ foley_status Encoder::create(const foley_encoder_config* c, int dev) {
         if (cfg.patch_size < 8 || cfg.patch_size % 8 != 0 || cfg.image_size % cfg.patch_size != 0 ||
             (3 * cfg.patch_size * cfg.patch_size) % 64 != 0)
             return fail(FOLEY_ERR_UNSUPPORTED, "SigLIP: patch size must be a multiple of 8 dividing the image size");
+    } else if (cfg.kind == FOLEY_ENC_SYNCHFORMER) {
+        if (cfg.patch_size != 16 || cfg.image_size != 224)
+            return fail(FOLEY_ERR_UNSUPPORTED, "Synchformer: MotionFormer divided_224_16x4 only (224 px, 16 x 16 x 2 tubelets)");
     } else {
         if (cfg.vocab_size < 1 || cfg.max_positions < 4) return fail(FOLEY_ERR_INVALID, "CLAP: vocabulary / positions");
     }
@@ -134,17 +154,28 @@ foley_status Encoder::create(const foley_encoder_config* c, int dev) {
     FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_null, cudaEventDisableTiming));
     std::string err;
     if (!gemm_init_attributes(&err)) return fail(FOLEY_ERR_CUDA, err);
-    FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
-    FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
+    FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_small_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     FOLEY_CUDA_OK(attention_tc64_init());
+    FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
+    FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_small_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     if (const char* e = getenv("FOLEY_ENC_ATT_TC")) att_tc = atoi(e);
     layers.resize(NL);
+    if (cfg.kind == FOLEY_ENC_SYNCHFORMER) sblocks.resize(NL);
     return FOLEY_OK;
 }
 
 // SigLIP checkpoints carry the text tower too, CLAP ones the pooler / projection: neither is on this path.
+static const char* kSyncPrefix = "vfeat_extractor.";
 bool Encoder::name_is_used(const std::string& n) const {
     if (cfg.kind == FOLEY_ENC_SIGLIP_VISION) return n.rfind("vision_model.", 0) == 0;
+    if (cfg.kind == FOLEY_ENC_SYNCHFORMER) {       // Synchformer state dict: the MotionFormer lives under vfeat_extractor.
+        const std::string m = n.rfind(kSyncPrefix, 0) == 0 ? n.substr(strlen(kSyncPrefix)) : n;
+        if (m.rfind("patch_embed.", 0) == 0) return false;           // 2-D patch embedding: unused by the video model
+        for (const char* p : {"cls_token", "pos_embed", "temp_embed", "patch_embed_3d.", "blocks.", "norm.", "spatial_attn_agg."})
+            if (m.rfind(p, 0) == 0) return true;
+        return false;
+    }
     if (n.rfind("text_model.", 0) != 0) return false;
     if (n.find(".pooler.") != std::string::npos) return false;
     if (n.find("position_ids") != std::string::npos || n.find("token_type_ids") != std::string::npos) return false;
@@ -152,11 +183,12 @@ bool Encoder::name_is_used(const std::string& n) const {
 }
 
 foley_status Encoder::load_tensor(const char* name, const void* data, const int64_t* shape, int ndim, int dtype) {
-    if (!name || !data || ndim < 0 || ndim > 4) return fail(FOLEY_ERR_INVALID, "encoder load_tensor: bad arguments");
+    if (!name || !data || ndim < 0 || ndim > 5) return fail(FOLEY_ERR_INVALID, "encoder load_tensor: bad arguments");
     if (dtype != FOLEY_DT_BF16 && dtype != FOLEY_DT_F32 && dtype != FOLEY_DT_F16)
         return fail(FOLEY_ERR_INVALID, "encoder load_tensor: dtype must be bf16, f32 or f16");
-    const std::string n(name);
+    std::string n(name);
     if (!name_is_used(n)) return FOLEY_OK;
+    if (cfg.kind == FOLEY_ENC_SYNCHFORMER && n.rfind(kSyncPrefix, 0) == 0) n = n.substr(strlen(kSyncPrefix));
     if (finalized) return fail(FOLEY_ERR_STATE, "encoder weights cannot be reloaded after finalize (create a new encoder)");
     FOLEY_CUDA_OK(cudaSetDevice(device));
     RawTensor rt;
@@ -184,7 +216,7 @@ foley_status Encoder::load_safetensors(const char* path, const char* prefix, int
         if (!name_is_used(name)) continue;
         const int dt = st_dtype_to_foley(e.dtype);
         if (dt < 0 || dt > FOLEY_DT_F16) return fail(FOLEY_ERR_UNSUPPORTED, "encoder load_safetensors: dtype " + e.dtype + " of " + e.name);
-        if (e.shape.size() > 4) return fail(FOLEY_ERR_INVALID, "encoder load_safetensors: rank > 4: " + e.name);
+        if (e.shape.size() > 5) return fail(FOLEY_ERR_INVALID, "encoder load_safetensors: rank > 5: " + e.name);
         ST_OK(load_tensor(name.c_str(), f.data + e.begin, e.shape.data(), static_cast<int>(e.shape.size()), dt));
         ++count;
     }
@@ -258,10 +290,66 @@ foley_status Encoder::take_qkv(const std::string& qn, const std::string& kn, con
     return FOLEY_OK;
 }
 
+// Linear of a module that runs under fp16 autocast with bf16 parameters: weight and bias reach the GEMM as fp16(bf16(w)).
+foley_status Encoder::take_linear_f16(const std::string& name, LinearW* out, int n_expected, int k_expected) {
+    ST_OK(take_linear(name, out, n_expected, k_expected));
+    const long long nw = static_cast<long long>(n_expected) * k_expected;
+    bf16_to_f16_kernel<<<enc_blocks(nw, 256), 256>>>(out->w, nw, reinterpret_cast<__half*>(out->w));     // in place: same element size
+    bf16_to_f16_kernel<<<enc_blocks(n_expected, 256), 256>>>(out->b, n_expected, reinterpret_cast<__half*>(out->b));
+    FOLEY_CUDA_OK(cudaGetLastError());
+    return FOLEY_OK;
+}
+foley_status Encoder::take_rows_f16(const std::string& wname, const std::string& bname, int n, int k, LinearW* out) {
+    ST_OK(take_rows(wname, bname, 0, n, k, out));
+    const long long nw = static_cast<long long>(n) * k;
+    bf16_to_f16_kernel<<<enc_blocks(nw, 256), 256>>>(out->w, nw, reinterpret_cast<__half*>(out->w));
+    bf16_to_f16_kernel<<<enc_blocks(n, 256), 256>>>(out->b, n, reinterpret_cast<__half*>(out->b));
+    FOLEY_CUDA_OK(cudaGetLastError());
+    return FOLEY_OK;
+}
+
 foley_status Encoder::finalize() {
     if (finalized) return FOLEY_OK;
     FOLEY_CUDA_OK(cudaSetDevice(device));
-    if (cfg.kind == FOLEY_ENC_SIGLIP_VISION) {
+    if (cfg.kind == FOLEY_ENC_SYNCHFORMER) {
+        const int P = cfg.patch_size, G = cfg.image_size / P, NSP = G * G;          // 196 spatial locations, 8 temporal positions
+        ST_OK(take_linear_f16("patch_embed_3d.proj", &s_patch, C, 3 * 2 * P * P));
+        bf16 *cls = nullptr, *pos = nullptr, *temp = nullptr, *acls = nullptr;
+        ST_OK(take_vec("cls_token", &cls, C));
+        ST_OK(take_vec("pos_embed", &pos, static_cast<int64_t>(1 + NSP) * C));
+        ST_OK(take_vec("temp_embed", &temp, 8LL * C));
+        const long long ntab = (1LL + 8LL * NSP) * C;
+        FOLEY_CUDA_OK(cudaMalloc(&s_tok_tab, ntab * sizeof(float)));
+        packed.push_back(s_tok_tab);
+        sync_token_table_kernel<<<enc_blocks(ntab, 256), 256>>>(cls, pos, temp, NSP, 8, C, s_tok_tab);
+        FOLEY_CUDA_OK(cudaGetLastError());
+        for (int i = 0; i < NL; ++i) {
+            const std::string l = "blocks." + std::to_string(i) + ".";
+            SyncBlockW& w = sblocks[i];
+            ST_OK(take_vec(l + "norm1.weight", &w.n1w, C)); ST_OK(take_vec(l + "norm1.bias", &w.n1b, C));
+            ST_OK(take_vec(l + "norm2.weight", &w.n2w, C)); ST_OK(take_vec(l + "norm2.bias", &w.n2b, C));
+            ST_OK(take_vec(l + "norm3.weight", &w.n3w, C)); ST_OK(take_vec(l + "norm3.bias", &w.n3b, C));
+            ST_OK(take_linear_f16(l + "timeattn.qkv", &w.qkv_t, 3 * C, C));
+            ST_OK(take_linear_f16(l + "timeattn.proj", &w.proj_t, C, C));
+            ST_OK(take_linear_f16(l + "attn.qkv", &w.qkv_s, 3 * C, C));
+            ST_OK(take_linear_f16(l + "attn.proj", &w.proj_s, C, C));
+            ST_OK(take_linear_f16(l + "mlp.fc1", &w.fc1, F, C));
+            ST_OK(take_linear_f16(l + "mlp.fc2", &w.fc2, C, F));
+        }
+        ST_OK(take_vec("norm.weight", &s_norm_w, C)); ST_OK(take_vec("norm.bias", &s_norm_b, C));
+        const std::string ag = "spatial_attn_agg.";
+        ST_OK(take_vec(ag + "cls_token", &acls, C));
+        FOLEY_CUDA_OK(cudaMalloc(&s_agg_cls, C * sizeof(float)));
+        packed.push_back(s_agg_cls);
+        bf16_to_f32_kernel<<<enc_blocks(C, 256), 256>>>(acls, C, s_agg_cls);
+        FOLEY_CUDA_OK(cudaGetLastError());
+        ST_OK(take_rows_f16(ag + "self_attn.in_proj_weight", ag + "self_attn.in_proj_bias", 3 * C, C, &s_in_proj));
+        ST_OK(take_linear_f16(ag + "self_attn.out_proj", &s_out_proj, C, C));
+        ST_OK(take_linear_f16(ag + "linear1", &s_lin1, F, C));
+        ST_OK(take_linear_f16(ag + "linear2", &s_lin2, C, F));
+        ST_OK(take_vec(ag + "norm1.weight", &s_an1w, C)); ST_OK(take_vec(ag + "norm1.bias", &s_an1b, C));
+        ST_OK(take_vec(ag + "norm2.weight", &s_an2w, C)); ST_OK(take_vec(ag + "norm2.bias", &s_an2b, C));
+    } else if (cfg.kind == FOLEY_ENC_SIGLIP_VISION) {
         const std::string vm = "vision_model.";
         const int P = cfg.patch_size, G = cfg.image_size / P;
         ST_OK(take_linear(vm + "embeddings.patch_embedding", &patch, C, 3 * P * P));
@@ -331,8 +419,14 @@ foley_status Encoder::ensure_rows(long long rows) {
         if (*p) { cudaFree(*p); *p = nullptr; }
     for (int** p : {&ids_dev, &pos_dev, &mask_dev})
         if (*p) { cudaFree(*p); *p = nullptr; }
+    for (float** p : {&xf, &xn})
+        if (*p) { cudaFree(*p); *p = nullptr; }
     cap_rows = 0;
     const size_t r = static_cast<size_t>(rows);
+    if (cfg.kind == FOLEY_ENC_SYNCHFORMER) {
+        FOLEY_CUDA_OK(cudaMalloc(&xf, r * C * sizeof(float)));
+        FOLEY_CUDA_OK(cudaMalloc(&xn, r * C * sizeof(float)));
+    }
     FOLEY_CUDA_OK(cudaMalloc(&x, r * C * 2));
     FOLEY_CUDA_OK(cudaMalloc(&h, r * C * 2));
     FOLEY_CUDA_OK(cudaMalloc(&qkv, r * 3 * C * 2));
@@ -348,7 +442,7 @@ foley_status Encoder::ensure_rows(long long rows) {
 
 // out[rows, N] = act(A[rows, K] W^T + b), bf16.  Tile width: the widest that still fills the SMs; big grids (the 40960-row
 // GEMMs of a 5 s clip) go to the persistent kernel (gemm_host.cuh).
-foley_status Encoder::gemm(cudaStream_t st, const bf16* A, long long rows, const LinearW& W, bf16* out, int act) {
+foley_status Encoder::gemm(cudaStream_t st, const bf16* A, long long rows, const LinearW& W, bf16* out, int act, int f16) {
     GemmLaunch L;
     L.a.ptr = A; L.a.dtype = DT_BF16; L.a.k = W.k; L.a.rows = rows; L.a.batch = 1; L.a.ld = W.k; L.a.batch_stride = rows * W.k;
     L.w = W.w; L.n = W.n; L.taps = 1; L.tap_off0 = 0; L.tap_stride = 1; L.splits = 1;
@@ -356,7 +450,7 @@ foley_status Encoder::gemm(cudaStream_t st, const bf16* A, long long rows, const
     int bn = 256;
     while (bn > 64 && mt * ((W.n + bn - 1) / bn) < num_sms) bn >>= 1;
     L.bn = bn;
-    L.epi.mode = EPI_BF16; L.epi.act = act; L.epi.out = out; L.epi.ldo = W.n; L.epi.bias = W.b;
+    L.epi.mode = EPI_BF16; L.epi.act = act; L.epi.out = out; L.epi.ldo = W.n; L.epi.bias = W.b; L.epi.f16 = f16;
     L.epi.out_batch_stride = rows * W.n;
     std::string err;
     if (!launch_gemm(L, st, &err)) return fail(FOLEY_ERR_CUDA, err);
@@ -370,12 +464,19 @@ foley_status Encoder::add_ln(cudaStream_t st, EncLnArgs a) {
     return FOLEY_OK;
 }
 
+foley_status Encoder::sync_ln(cudaStream_t st, SyncLnArgs a) {
+    a.eps = cfg.layer_norm_eps;
+    FOLEY_CUDA_OK(launch_k(sync_add_ln_kernel<3>, dim3(enc_blocks(a.rows, 8)), dim3(256), 0, st, a));
+    ++launches;
+    return FOLEY_OK;
+}
+
 foley_status Encoder::attention(cudaStream_t st, const EncAttnArgs& a, bool small) {
     if (small) {
         const size_t smem = static_cast<size_t>(ESA_WARPS) * a.Sk * sizeof(float);
         if (smem > 64 * 1024) return fail(FOLEY_ERR_UNSUPPORTED, "small attention: too many keys");
         const long long units = static_cast<long long>(a.B) * a.H * a.Sq;
-        FOLEY_CUDA_OK(launch_k(enc_small_attention_kernel, dim3(enc_blocks(units, ESA_WARPS)), dim3(32 * ESA_WARPS), smem, st, a));
+        FOLEY_CUDA_OK(launch_k(enc_small_attention_kernel<false>, dim3(enc_blocks(units, ESA_WARPS)), dim3(32 * ESA_WARPS), smem, st, a));
     } else if (att_tc) {
         AttTc64Args t;
         t.o = a.o; t.o_batch_stride = a.o_batch_stride; t.o_row_stride = a.o_row_stride; t.H = a.H; t.Sq = a.Sq; t.Sk = a.Sk;
@@ -385,7 +486,7 @@ foley_status Encoder::attention(cudaStream_t st, const EncAttnArgs& a, bool smal
             return fail(FOLEY_ERR_CUDA, err);
     } else {
         dim3 grid((a.Sq + EA_BM - 1) / EA_BM, a.H, a.B);
-        FOLEY_CUDA_OK(launch_k(enc_attention_kernel, grid, dim3(32 * EA_NW), EA_SMEM, st, a));
+        FOLEY_CUDA_OK(launch_k(enc_attention_kernel<false>, grid, dim3(32 * EA_NW), EA_SMEM, st, a));
     }
     ++launches;
     return FOLEY_OK;
@@ -519,6 +620,137 @@ foley_status Encoder::clap_encode(const int32_t* ids, const int32_t* mask, int B
     return FOLEY_OK;
 }
 
+// encode_video_with_sync (feature_utils.py:81-106) + Synchformer.forward -> MotionFormer.forward (motionformer.py:178-213):
+// frames fp32 [n_frames, 3, 224, 224] (25 fps, preprocessed) -> out fp32 [segments * 8, C], segments = (n_frames - 16) / 8 + 1
+// windows of 16 frames every 8 frames; per window 8 x 14 x 14 tubelet tokens + a class token through 12 divided space-time
+// blocks, the final norm, and one spatial aggregation layer (class token per temporal position).
+foley_status Encoder::synchformer_encode(const float* frames, int n_frames, float* out, cudaStream_t st) {
+    if (cfg.kind != FOLEY_ENC_SYNCHFORMER) return fail(FOLEY_ERR_STATE, "not a Synchformer encoder");
+    if (!finalized) return fail(FOLEY_ERR_STATE, "encoder used before finalize");
+    if (!frames || !out || n_frames < 16) return fail(FOLEY_ERR_INVALID, "synchformer_encode: needs at least 16 frames");
+    FOLEY_CUDA_OK(cudaSetDevice(device));
+    const int P = cfg.patch_size, IMG = cfg.image_size, G = IMG / P, NSP = G * G, NTOK = 1 + 8 * NSP, SEQ = 1 + NSP;
+    const int S = (n_frames - 16) / 8 + 1;
+    const int per_pass = cfg.max_frames_per_pass > 0 ? cfg.max_frames_per_pass : 16;     // segments per pass
+    ST_OK(ensure_rows(static_cast<long long>(std::min(per_pass, S)) * 8 * SEQ));         // 8 * 197 > 1569 rows per segment
+    const int nl = layers_run >= 0 ? std::min(layers_run, NL) : NL;
+    __half* hh = reinterpret_cast<__half*>(h);
+    __half* hy = reinterpret_cast<__half*>(y);
+    __half* hqkv = reinterpret_cast<__half*>(qkv);
+    __half* hatt = reinterpret_cast<__half*>(att);
+    for (int s0 = 0; s0 < S; s0 += per_pass) {
+        const int Sc = std::min(per_pass, S - s0);
+        const long long rows = static_cast<long long>(Sc) * NTOK;
+        const float* fr = frames + static_cast<long long>(s0) * 8 * 3 * IMG * IMG;
+        // ---- tubelet embedding: Conv3d as im2col + GEMM (fp16), class token + position / temporal tables (fp32)
+        const long long n8 = static_cast<long long>(Sc) * 8 * 2 * 3 * IMG * (IMG / 8);
+        FOLEY_CUDA_OK(launch_k(sync_patchify_kernel, dim3(enc_blocks(n8, 256)), dim3(256), 0, st, fr, Sc, IMG, P, reinterpret_cast<__half*>(mlp)));
+        ++launches;
+        ST_OK(gemm(st, mlp, static_cast<long long>(Sc) * 8 * NSP, s_patch, y, ACT_NONE, 1));
+        {
+            SyncLnArgs a;
+            a.patch = hy; a.tok_tab = s_tok_tab; a.tokens = NTOK; a.x_dst = xf; a.rows = rows; a.h_out = hh;
+            a.ln_w = nl > 0 ? sblocks[0].n3w : s_norm_w; a.ln_b = nl > 0 ? sblocks[0].n3b : s_norm_b;
+            if (nl == 0) { a.h_out = nullptr; a.n_out = xn; a.n_out_skip = NTOK; }
+            ST_OK(sync_ln(st, a));
+        }
+        auto cls_attention = [&]() -> foley_status {       // the class token attends to every token of its segment
+            EncAttnArgs ca;
+            ca.q = qkv; ca.k = qkv + C; ca.v = qkv + 2 * C; ca.o = att;
+            ca.B = Sc; ca.H = H; ca.Sq = 1; ca.Sk = NTOK;
+            ca.q_row_stride = ca.kv_row_stride = 3LL * C; ca.q_batch_stride = ca.kv_batch_stride = 3LL * C * NTOK;
+            ca.o_row_stride = C; ca.o_batch_stride = static_cast<long long>(C) * NTOK;
+            ca.scale = 0.125f; ca.round_scores = 1;
+            const size_t smem = static_cast<size_t>(ESA_WARPS) * ca.Sk * sizeof(float);
+            FOLEY_CUDA_OK(launch_k(enc_small_attention_kernel<true>, dim3(enc_blocks(static_cast<long long>(Sc) * H, ESA_WARPS)), dim3(32 * ESA_WARPS), smem, st, ca));
+            ++launches;
+            return FOLEY_OK;
+        };
+        for (int i = 0; i < nl; ++i) {
+            const SyncBlockW& w = sblocks[i];
+            // -- divided TIME attention (norm3 -> timeattn), vit_helper.py:155-158
+            ST_OK(gemm(st, h, rows, w.qkv_t, qkv, ACT_NONE, 1));
+            ST_OK(cls_attention());
+            FOLEY_CUDA_OK(launch_k(sync_time_attention_kernel, dim3(enc_blocks(static_cast<long long>(Sc) * NSP * H, 4)), dim3(128), 0, st,
+                                   static_cast<const __half*>(hqkv), hatt, Sc, NTOK, NSP, H, 0.125f));
+            ++launches;
+            ST_OK(gemm(st, att, rows, w.proj_t, y, ACT_NONE, 1));
+            {
+                SyncLnArgs a;
+                a.x = xf; a.y = hy; a.x_dst = xf; a.ln_w = w.n1w; a.ln_b = w.n1b; a.h_out = hh; a.rows = rows;
+                ST_OK(sync_ln(st, a));
+            }
+            // -- divided SPACE attention (norm1 -> attn), vit_helper.py:160-163
+            ST_OK(gemm(st, h, rows, w.qkv_s, qkv, ACT_NONE, 1));
+            ST_OK(cls_attention());
+            {
+                EncAttnArgs sa;       // frame b2 of segment b1: 196 queries, keys = [class token; the 196 tokens of the frame]
+                sa.q = qkv + 3LL * C; sa.k = qkv + C; sa.v = qkv + 2 * C; sa.o = att + C;
+                sa.B = Sc * 8; sa.batch2 = 8; sa.H = H; sa.Sq = NSP; sa.Sk = SEQ;
+                sa.q_row_stride = sa.kv_row_stride = 3LL * C;
+                sa.q_batch_stride = sa.kv_batch_stride = 3LL * C * NTOK; sa.q_batch_stride2 = 3LL * C * NSP;
+                sa.kv_batch_stride2 = NSP;                                   // rows
+                sa.o_row_stride = C; sa.o_batch_stride = static_cast<long long>(C) * NTOK; sa.o_batch_stride2 = static_cast<long long>(C) * NSP;
+                sa.scale = 0.125f; sa.round_scores = 1;
+                dim3 grid((sa.Sq + EA_BM - 1) / EA_BM, sa.H, sa.B);
+                FOLEY_CUDA_OK(launch_k(enc_attention_kernel<true>, grid, dim3(32 * EA_NW), EA_SMEM, st, sa));
+                ++launches;
+            }
+            ST_OK(gemm(st, att, rows, w.proj_s, y, ACT_NONE, 1));
+            {
+                SyncLnArgs a;
+                a.x = xf; a.y = hy; a.x_dst = xf; a.ln_w = w.n2w; a.ln_b = w.n2b; a.h_out = hh; a.rows = rows;
+                ST_OK(sync_ln(st, a));
+            }
+            // -- MLP (norm2 -> fc1 -> GELU -> fc2)
+            ST_OK(gemm(st, h, rows, w.fc1, mlp, ACT_GELU_ERF, 1));
+            ST_OK(gemm(st, mlp, rows, w.fc2, y, ACT_NONE, 1));
+            {
+                SyncLnArgs a;
+                const bool last = i + 1 == nl;
+                a.x = xf; a.y = hy; a.x_dst = xf; a.rows = rows;
+                if (!last) { a.ln_w = sblocks[i + 1].n3w; a.ln_b = sblocks[i + 1].n3b; a.h_out = hh; }
+                else { a.ln_w = s_norm_w; a.ln_b = s_norm_b; a.n_out = xn; a.n_out_skip = NTOK; }   // x[:, 1:] -> norm (motionformer.py:186-187)
+                ST_OK(sync_ln(st, a));
+            }
+        }
+        // ---- spatial aggregation layer (SpatialTransformerEncoderLayer, motionformer.py:330-355: nn.TransformerEncoderLayer,
+        // norm_first, a class token per (segment, temporal position); only the class-token row leaves the layer)
+        const long long rows_a = static_cast<long long>(Sc) * 8 * SEQ, nseq = static_cast<long long>(Sc) * 8;
+        {
+            SyncLnArgs a;
+            a.seq_src = xn; a.seq_cls = s_agg_cls; a.seq_len = SEQ; a.ln_w = s_an1w; a.ln_b = s_an1b; a.h_out = hh; a.rows = rows_a;
+            ST_OK(sync_ln(st, a));
+        }
+        ST_OK(gemm(st, h, rows_a, s_in_proj, qkv, ACT_NONE, 1));
+        {
+            EncAttnArgs ca;
+            ca.q = qkv; ca.k = qkv + C; ca.v = qkv + 2 * C; ca.o = att;
+            ca.B = static_cast<int>(nseq); ca.H = H; ca.Sq = 1; ca.Sk = SEQ;
+            ca.q_row_stride = ca.kv_row_stride = 3LL * C; ca.q_batch_stride = ca.kv_batch_stride = 3LL * C * SEQ;
+            ca.o_row_stride = C; ca.o_batch_stride = C;
+            ca.scale = 0.125f;
+            const size_t smem = static_cast<size_t>(ESA_WARPS) * ca.Sk * sizeof(float);
+            FOLEY_CUDA_OK(launch_k(enc_small_attention_kernel<true>, dim3(enc_blocks(nseq * H, ESA_WARPS)), dim3(32 * ESA_WARPS), smem, st, ca));
+            ++launches;
+        }
+        ST_OK(gemm(st, att, nseq, s_out_proj, y, ACT_NONE, 1));
+        {
+            SyncLnArgs a;       // x1 = cls + sa(...): the class-token rows of the layer's residual stream
+            a.seq_cls = s_agg_cls; a.seq_len = 0; a.y = hy; a.x_dst = xf; a.ln_w = s_an2w; a.ln_b = s_an2b; a.h_out = hh; a.rows = nseq;
+            ST_OK(sync_ln(st, a));
+        }
+        ST_OK(gemm(st, h, nseq, s_lin1, mlp, ACT_GELU_ERF, 1));
+        ST_OK(gemm(st, mlp, nseq, s_lin2, y, ACT_NONE, 1));
+        {
+            SyncLnArgs a;
+            a.x = xf; a.y = hy; a.x_dst = out + static_cast<long long>(s0) * 8 * C; a.rows = nseq;
+            ST_OK(sync_ln(st, a));
+        }
+    }
+    return FOLEY_OK;
+}
+
 __global__ void enc_bf16_to_f32_kernel(const __nv_bfloat16* src, long long n, float* dst) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = __bfloat162float(src[i]);
@@ -612,6 +844,14 @@ extern "C" foley_status foley_clap_text_encode(foley_encoder* e, const int32_t* 
     return e->impl.order_after(stream);
     ENC_GUARD_END
 }
+extern "C" foley_status foley_synchformer_encode(foley_encoder* e, const float* frames, int32_t n_frames, float* out, void* stream) {
+    if (!e) return fail(FOLEY_ERR_INVALID, "null encoder");
+    ENC_GUARD_BEGIN
+    foley_status s = e->impl.synchformer_encode(frames, n_frames, out, e->impl.pick_stream(stream));
+    if (s != FOLEY_OK) return s;
+    return e->impl.order_after(stream);
+    ENC_GUARD_END
+}
 extern "C" foley_status foley_encoder_set_option(foley_encoder* e, const char* key, int64_t value) {
     if (!e || !key) return fail(FOLEY_ERR_INVALID, "foley_encoder_set_option: null argument");
     const std::string k(key);
@@ -644,8 +884,8 @@ extern "C" foley_status foley_attention_d64(const void* q, const void* k, const 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static bool attr = false;
     if (!attr) {
-        FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
-        FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
+        FOLEY_CUDA_OK(cudaFuncSetAttribute(enc_small_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         FOLEY_CUDA_OK(attention_tc64_init());
         attr = true;
     }
@@ -662,10 +902,10 @@ extern "C" foley_status foley_attention_d64(const void* q, const void* k, const 
         const size_t smem = static_cast<size_t>(ESA_WARPS) * Sk * sizeof(float);
         if (smem > 64 * 1024) return fail(FOLEY_ERR_UNSUPPORTED, "foley_attention_d64: too many keys for the small kernel");
         const long long units = static_cast<long long>(batch) * heads * Sq;
-        FOLEY_CUDA_OK(launch_k(enc_small_attention_kernel, dim3(enc_blocks(units, ESA_WARPS)), dim3(32 * ESA_WARPS), smem, st, a));
+        FOLEY_CUDA_OK(launch_k(enc_small_attention_kernel<false>, dim3(enc_blocks(units, ESA_WARPS)), dim3(32 * ESA_WARPS), smem, st, a));
     } else {
         dim3 grid((Sq + EA_BM - 1) / EA_BM, heads, batch);
-        FOLEY_CUDA_OK(launch_k(enc_attention_kernel, grid, dim3(32 * EA_NW), EA_SMEM, st, a));
+        FOLEY_CUDA_OK(launch_k(enc_attention_kernel<false>, grid, dim3(32 * EA_NW), EA_SMEM, st, a));
     }
     return FOLEY_OK;
 }

@@ -48,7 +48,9 @@ struct GemmEpi {
     long long ldo = 0;              // elements between output rows
     long long out_batch_stride = 0; // elements between samples
     long long split_stride = 0;     // EPI_F32: elements between K-split partials
-    const void* bias = nullptr;     // bf16[N] (DiT) or fp32[ch_mod] (DAC); may be null
+    const void* bias = nullptr;     // bf16[N] (DiT; fp16[N] with f16) or fp32[ch_mod] (DAC); may be null
+    int f16 = 0;                    // EPI_BF16 only: operands, bias and output are IEEE fp16 instead of bf16 (same 16-bit layouts and
+                                    // tensor maps; kind::f16 instruction descriptor format 0) — the Synchformer runs under fp16 autocast
     // --- EPI_DAC only
     void* out2 = nullptr;           // snake(y) with alpha (next conv's input); may be null
     const float* resid = nullptr;   // residual input, same indexing as out; may be null
@@ -303,7 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             }
         }
         if (lane == 0 && leader) {
-            constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, kPair ? 2 * Cfg::BM : Cfg::BM, BN);
+            const uint32_t idesc = make_idesc(kTF32 ? 2 : (g.epi.f16 ? 0 : 1), kPair ? 2 * Cfg::BM : Cfg::BM, BN);
             int s = -1;
             uint32_t ph = 1;
             for (int i = 0; i < num_kb; ++i) {
@@ -370,7 +372,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                         if (e.bias) bv = reinterpret_cast<const float*>(e.bias)[ch];
                         if (e.alpha) { al = e.alpha[ch]; ial = 1.0f / (al + 1e-9f); }
                     } else if (e.bias) {
-                        bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.bias)[col]);
+                        bv = e.f16 ? __half2float(reinterpret_cast<const __half*>(e.bias)[col])
+                                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.bias)[col]);
                     }
                 }
                 epi_f[c] = bv; epi_f[256 + c] = al; epi_f[512 + c] = ial;
@@ -431,6 +434,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     a[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + __uint_as_float(b1);
                     a[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + __uint_as_float(b2);
                     a[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + __uint_as_float(b3);
+                }
+                if (e.f16) {      // fp16 module (Synchformer under autocast): nn.GELU() or no activation
+                    if (e.act == ACT_GELU_ERF) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { const float x = f16_round(a[j]); a[j] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+                    } else if (e.act != ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) a[j] = apply_act(f16_round(a[j]), e.act);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        st_shared_v4(row_addr + (((piece0 + j) ^ sw) << 4), pack_f16x2(a[8 * j], a[8 * j + 1]), pack_f16x2(a[8 * j + 2], a[8 * j + 3]),
+                                     pack_f16x2(a[8 * j + 4], a[8 * j + 5]), pack_f16x2(a[8 * j + 6], a[8 * j + 7]));
+                    return;
                 }
                 if (e.act == ACT_SILU) {
 #pragma unroll

@@ -122,7 +122,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     } else if (warp == 1) {
         // ------------------------------------------------------------- MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(1, Cfg::BM, Cfg::BN);
+            const uint32_t idesc = make_idesc(g.epi.f16 ? 0 : 1, Cfg::BM, Cfg::BN);
             int s = 0;
             uint32_t ph = 0;
             int j = 0;   // local tile counter
@@ -202,7 +202,18 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                             float a[32];
 #pragma unroll
                             for (int jj = 0; jj < 32; ++jj) a[jj] = __uint_as_float(v[jj]);
-                            if (bias) {
+                            if (bias && e.f16) {
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
+                                    const uint4 bw = __ldg(reinterpret_cast<const uint4*>(bias + n0 + c0) + jj);
+                                    const __half2* b2 = reinterpret_cast<const __half2*>(&bw);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        a[8 * jj + 2 * k] += __low2float(b2[k]);
+                                        a[8 * jj + 2 * k + 1] += __high2float(b2[k]);
+                                    }
+                                }
+                            } else if (bias) {
 #pragma unroll
                                 for (int jj = 0; jj < 4; ++jj) {
                                     const uint4 bw = __ldg(reinterpret_cast<const uint4*>(bias + n0 + c0) + jj);
@@ -214,7 +225,15 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                                     }
                                 }
                             }
-                            if (e.act == ACT_SILU) {
+                            if (e.f16) {
+                                if (e.act == ACT_GELU_ERF) {
+#pragma unroll
+                                    for (int jj = 0; jj < 32; ++jj) { const float x = f16_round(a[jj]); a[jj] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+                                } else if (e.act != ACT_NONE) {
+#pragma unroll
+                                    for (int jj = 0; jj < 32; ++jj) a[jj] = apply_act(f16_round(a[jj]), e.act);
+                                }
+                            } else if (e.act == ACT_SILU) {
 #pragma unroll
                                 for (int jj = 0; jj < 32; ++jj) { const float x = bf16_round(a[jj]); a[jj] = __fdividef(x, 1.0f + __expf(-x)); }
                             } else if (e.act == ACT_GELU_TANH) {
@@ -226,7 +245,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                             }
                             uint32_t packed[16];
 #pragma unroll
-                            for (int jj = 0; jj < 16; ++jj) packed[jj] = pack_bf16x2(a[2 * jj], a[2 * jj + 1]);
+                            for (int jj = 0; jj < 16; ++jj) packed[jj] = e.f16 ? pack_f16x2(a[2 * jj], a[2 * jj + 1]) : pack_bf16x2(a[2 * jj], a[2 * jj + 1]);
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj)
                                 st_shared_v4(row_addr + (((piece0 + jj) ^ sw) << 4), packed[4 * jj], packed[4 * jj + 1],

@@ -356,6 +356,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 #endif
+__device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_tanh_f(float x) {
     // tanh(u) = 1 - 2 / (1 + e^{2u}) on the fast exp / divide units (abs error ~1e-6, far below the bf16 rounding

@@ -14,7 +14,7 @@ import torch
 
 from .engine import FOLEY_DT, FoleyError, _check, _stream_ptr, load_library
 
-ENC_SIGLIP_VISION, ENC_CLAP_TEXT = 0, 1
+ENC_SIGLIP_VISION, ENC_CLAP_TEXT, ENC_SYNCHFORMER = 0, 1, 2
 
 
 class _EncConfig(ctypes.Structure):
@@ -28,6 +28,8 @@ class _EncConfig(ctypes.Structure):
 # reference's Dependencies Loader names (nodes.py:199-201)
 SIGLIP2_BASE_512 = dict(hidden_size=768, num_heads=12, num_layers=12, intermediate_size=3072, layer_norm_eps=1e-6,
                         image_size=512, patch_size=16)
+MOTIONFORMER_DIVIDED_224 = dict(hidden_size=768, num_heads=12, num_layers=12, intermediate_size=3072, layer_norm_eps=1e-6,
+                                image_size=224, patch_size=16)      # models/synchformer/divided_224_16x4.yaml
 CLAP_TEXT_GENERAL = dict(hidden_size=768, num_heads=12, num_layers=12, intermediate_size=3072, layer_norm_eps=1e-12,
                          vocab_size=50265, max_positions=514, pad_token_id=1)
 
@@ -46,6 +48,7 @@ def _lib():
         lib.foley_encoder_finalize.argtypes = [c_void_p]
         lib.foley_siglip_encode.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
         lib.foley_clap_text_encode.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32), c_int32, c_int32, c_void_p, c_void_p]
+        lib.foley_synchformer_encode.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
         lib.foley_encoder_set_option.argtypes = [c_void_p, c_char_p, c_int64]
         lib.foley_encoder_launch_count.argtypes = [c_void_p]
         lib.foley_encoder_launch_count.restype = c_int64
@@ -200,6 +203,38 @@ class ClapTextEncoder(_Encoder):
         out = torch.empty(B, T, self.cfg.hidden_size, dtype=torch.bfloat16, device=self.device)
         _check(self.lib.foley_clap_text_encode(self._h, ctypes.cast(ids.data_ptr(), POINTER(c_int32)), mask_p, B, T,
                                                c_void_p(out.data_ptr()), _stream_ptr(self.device)))
+        return out
+
+
+class SynchformerEncoder(_Encoder):
+    """The Synchformer visual extractor (reference models/synchformer: MotionFormer, divided space-time attention + spatial
+    aggregation layer) on the engine's kernels, with the arithmetic of the reference's call: fp16 autocast around a module
+    whose parameters are in the DiT's dtype (feature_utils.py:81-106, nodes.py:283-284)."""
+    KIND = ENC_SYNCHFORMER
+    DEFAULTS = MOTIONFORMER_DIVIDED_224
+
+    @classmethod
+    def from_state_dict(cls, sd, device=None, **cfg):
+        """sd: Synchformer state dict (keys `vfeat_extractor.*`; the audio extractor / sync head are ignored) or a bare
+        MotionFormer state dict."""
+        enc = cls(cfg or None, device=device)
+        enc.load_state_dict(sd)
+        return enc.finalize()
+
+    def encode(self, frames):
+        """frames: fp32 [T25, 3, 224, 224] on this device (preprocess.preprocess_video's 25 fps output) -> fp32
+        [1, segments * 8, hidden], segments = (T25 - 16) // 8 + 1 (encode_video_with_sync's `b (s t) d`)."""
+        if not self._finalized:
+            self.finalize()
+        fr = frames.to(self.device, torch.float32).contiguous()
+        if fr.dim() != 4 or tuple(fr.shape[1:]) != (3, 224, 224):
+            raise FoleyError(f"frames have shape {tuple(fr.shape)}, expected [T, 3, 224, 224]")
+        if fr.shape[0] < 16:
+            raise FoleyError("the Synchformer needs at least 16 frames (one 0.64 s window)")
+        S = (fr.shape[0] - 16) // 8 + 1
+        out = torch.empty(1, S * 8, self.cfg.hidden_size, dtype=torch.float32, device=self.device)
+        _check(self.lib.foley_synchformer_encode(self._h, c_void_p(fr.data_ptr()), fr.shape[0], c_void_p(out.data_ptr()),
+                                                 _stream_ptr(self.device)))
         return out
 
 

@@ -1,10 +1,10 @@
 """The condition encoders behind the Sampler (reference nodes.py:283-351, utils.py:262-292, feature_utils.py:64-138).
 
-SigLIP2 (google/siglip2-base-patch16-512) and the CLAP text tower (laion/larger_clap_general) run ON THE ENGINE
-(encoders.py -> csrc/encoders.cu): their weights go from the HF snapshot's model.safetensors straight to the device, no
-torch module is built.  The tokenizer is HF's (host-side string work).  Synchformer (MotionFormer under fp16 autocast,
-feature_utils.py:81-106) is NOT built: it is borrowed from the reference's `hunyuanvideo_foley` package when that is
-installed; without it text-to-audio still works and video-to-audio raises with the reason.
+All three run ON THE ENGINE (encoders.py -> csrc/encoders.cu): SigLIP2 (google/siglip2-base-patch16-512) and the CLAP text
+tower (laion/larger_clap_general) take their weights from the HF snapshot's model.safetensors straight to the device, the
+Synchformer visual extractor (MotionFormer under fp16 autocast, feature_utils.py:81-106) from the checkpoint the
+Dependencies Loader names; no torch module is built and the reference's model package is not needed.  The tokenizer is HF's
+(host-side string work).
 
 `load_extractors(...)` returns the `deps` entries the Dependencies Loader publishes (same keys as reference
 nodes.py:176-201) plus `extract_features(pre_8fps, pre_25fps, prompt, negative_prompt) -> (visual_feats, text_feats,
@@ -82,31 +82,25 @@ def load_clap_text(device, repo=CLAP_REPO):
 
 
 def load_synchformer(synchformer_path, device, load_torch_file):
-    """Borrowed: the reference's Synchformer module (nodes.py:176-181).  Returns (module, encode fn) or (None, reason)."""
-    try:
-        from hunyuanvideo_foley.models.synchformer import Synchformer          # reference package, if installed
-        from hunyuanvideo_foley.utils.feature_utils import encode_video_with_sync
-    except Exception as e:  # noqa: BLE001
-        return None, f"the reference package `hunyuanvideo_foley` is not importable ({e})"
+    """The Synchformer visual extractor on the engine, from the reference's checkpoint (nodes.py:176-181: `load_torch_file`
+    + `load_state_dict(strict=False)`; keys `vfeat_extractor.*`, everything else is ignored by name)."""
+    from .encoders import SynchformerEncoder
     sd = load_torch_file(synchformer_path, device=torch.device("cpu"))
     if isinstance(sd, dict) and "state_dict" in sd and not any(torch.is_tensor(v) for v in sd.values()):
         sd = sd["state_dict"]
-    model = Synchformer()
-    model.load_state_dict(sd, strict=False)
-    return model.to(device).eval(), encode_video_with_sync
+    return SynchformerEncoder.from_state_dict(sd, device=device)
 
 
 def make_extract_features(siglip2, clap_tokenizer, clap_text, sync_encode, device, max_text_tokens=None):
     """The one callable the Sampler needs.  siglip2 / clap_text: objects with `.encode` (encoders.py);
-    sync_encode(frames [1, T25, 3, 224, 224]) -> [1, S, 768], or a string saying why Synchformer is unavailable."""
+    sync_encode(frames [1, T25, 3, 224, 224]) -> [1, S, 768], or a string saying why no Synchformer is available."""
     def extract_features(pre_8fps, pre_25fps, prompt, negative_prompt):
         """pre_8fps [T8,3,512,512] / pre_25fps [T25,3,224,224]: encoder inputs preprocessed on the GPU
         (preprocess.preprocess_video), or None for text-to-audio."""
         visual, audio_len = {}, None
         if pre_8fps is not None:
             if isinstance(sync_encode, str):
-                raise FoleyError("video-to-audio needs the Synchformer encoder, which foley_b200 borrows from the reference "
-                                 f"node pack: {sync_encode}")
+                raise FoleyError(f"video-to-audio needs the Synchformer encoder: {sync_encode}")
             visual["siglip2_feat"] = siglip2.encode(pre_8fps.to(device)).unsqueeze(0)        # [1, T8, 768] (feature_utils.py:77-78)
             visual["syncformer_feat"] = sync_encode(pre_25fps.unsqueeze(0).to(device))
             audio_len = pre_25fps.shape[0] / 25.0                                             # utils.py:281
@@ -125,23 +119,21 @@ def load_extractors(synchformer_path, device, load_torch_file):
     from .config import AttributeDict
     siglip2 = load_siglip2(device)
     clap_tokenizer, clap_text = load_clap_text(device)
-    sync_model, sync_fn = load_synchformer(synchformer_path, device, load_torch_file)
+    sync = load_synchformer(synchformer_path, device, load_torch_file)
     siglip2_preprocess, syncformer_preprocess = _v2_pipelines()
     deps = AttributeDict({
-        "syncformer_model": sync_model,
+        "syncformer_model": sync,              # engine encoders (.encode), not torch modules
         "siglip2_preprocess": siglip2_preprocess,
         "syncformer_preprocess": syncformer_preprocess,
-        "siglip2_model": siglip2,              # engine encoder (.encode), not the HF module
+        "siglip2_model": siglip2,
         "clap_tokenizer": clap_tokenizer,
-        "clap_model": clap_text,               # engine encoder (.encode), not the HF module
+        "clap_model": clap_text,
         "device": device,
     })
-    if sync_model is None:
-        logger.warning("Synchformer unavailable (%s): text-to-audio only", sync_fn)
-        sync_encode = sync_fn
-    else:
-        def sync_encode(frames):
-            return sync_fn(frames, deps)
+
+    def sync_encode(frames):                   # [1, T25, 3, 224, 224] -> [1, S * 8, 768]  (encode_video_with_sync)
+        return sync.encode(frames[0])
+
     out = dict(deps)
     out["extract_features"] = make_extract_features(siglip2, clap_tokenizer, clap_text, sync_encode, device,
                                                     max_text_tokens=clap_text.config["max_positions"] - 2)

@@ -7,10 +7,10 @@ what flows through HUNYUAN_MODEL / dac_model: handles to the B200 engine instead
 
   * torch.compile and BlockSwap nodes are accepted and ignored (north-star: no torch.compile path, no
     block-swap / CPU-offload fallback; 10.3 GB of bf16 weights fit a B200's 180 GB).
-  * The condition encoders (reference nodes.py:283-351): SigLIP2 and the CLAP text tower run on the engine
-    (encoders.py, csrc/encoders.cu; weights straight from the HF snapshots, tokenizer HF's); Synchformer is borrowed from
-    the reference's model package when it is installed next to this one (feature_bridge.py).  `deps` can also be populated
-    by the caller with any callable `extract_features` (tests and bench use seeded stubs).
+  * The condition encoders (reference nodes.py:283-351) — SigLIP2, the Synchformer visual extractor and the CLAP text
+    tower — run on the engine (encoders.py, csrc/encoders.cu; weights straight from the HF snapshots / the Synchformer
+    checkpoint, tokenizer HF's; feature_bridge.py).  `deps` can also be populated by the caller with any callable
+    `extract_features` (tests and bench use seeded stubs).
 """
 import logging
 import os
@@ -296,8 +296,7 @@ class HunyuanDependenciesLoader:
         if isinstance(vae_sd, dict) and "state_dict" in vae_sd:
             vae_sd = vae_sd["state_dict"]
         deps["dac_model"] = FoleyDAC.from_state_dict(vae_sd, device=device)
-        # Condition encoders: SigLIP2 + CLAP text run on the engine (encoders.py), the tokenizer is HF's, Synchformer is
-        # borrowed from the reference node pack when it is installed (feature_bridge.py).
+        # Condition encoders: SigLIP2, Synchformer and CLAP text all run on the engine (encoders.py); the tokenizer is HF's.
         try:
             from .feature_bridge import load_extractors
             deps.update(load_extractors(folder_paths.get_full_path("foley", synchformer_name), device, load_torch_file))
@@ -305,7 +304,7 @@ class HunyuanDependenciesLoader:
             raise
         except Exception as e:  # noqa: BLE001
             raise FoleyError("loading the condition encoders failed: the SigLIP2 / CLAP weights and tokenizer come from their "
-                             f"HF snapshots (transformers), Synchformer from the reference node pack ({e})") from e
+                             f"HF snapshots (transformers), the Synchformer weights from the selected checkpoint ({e})") from e
         deps["device"] = device
         return (AttributeDict(deps),)
 

@@ -253,7 +253,7 @@ foley_status foley_attention(const foley_attn_args* args, void* stream);
  * ("vision_model.encoder.layers.3.self_attn.q_proj.weight", "text_model.encoder.layer.0.attention.self.query.weight",
  * ...) from host tensors or straight from the model.safetensors of the HF snapshot; tensors of modules the path does
  * not run (SigLIP text tower, CLAP pooler / projection) are accepted and ignored. */
-enum { FOLEY_ENC_SIGLIP_VISION = 0, FOLEY_ENC_CLAP_TEXT = 1 };
+enum { FOLEY_ENC_SIGLIP_VISION = 0, FOLEY_ENC_CLAP_TEXT = 1, FOLEY_ENC_SYNCHFORMER = 2 };
 typedef struct foley_encoder_config {
     int32_t kind;                 /* FOLEY_ENC_* */
     int32_t hidden_size;          /* 768 */
@@ -283,6 +283,15 @@ foley_status foley_siglip_encode(foley_encoder* e, const float* pixels, int32_t 
  * padded positions included exactly as the reference passes them on. */
 foley_status foley_clap_text_encode(foley_encoder* e, const int32_t* ids, const int32_t* mask, int32_t batch, int32_t T,
                                     void* out, void* stream);
+/* encode_video_with_sync (feature_utils.py:81-106) -> Synchformer.forward -> MotionFormer (models/synchformer/motionformer.py,
+ * video_model_builder.py, vit_helper.py; config divided_224_16x4): frames = DEVICE fp32 [n_frames, 3, 224, 224] (the 25 fps
+ * output of foley_preprocess_frames); windows of 16 frames every 8 frames, segments = (n_frames - 16) / 8 + 1;
+ * out = DEVICE fp32 [segments * 8, hidden] (the reference's `(b s) 1 t d -> b (s t) d`).  Arithmetic as the reference runs it:
+ * fp16 autocast around a module whose parameters are in the DiT's dtype (fp16 GEMMs, fp32 LayerNorm / softmax / residual).
+ * Weights under the Synchformer state-dict names ("vfeat_extractor.blocks.0.timeattn.qkv.weight", ...; the audio extractor and
+ * the sync head are ignored).  kind FOLEY_ENC_SYNCHFORMER: hidden 768, 12 heads, 12 layers, intermediate 3072, eps 1e-6,
+ * image_size 224, patch_size 16; max_frames_per_pass = SEGMENTS per pass here (0 = 16). */
+foley_status foley_synchformer_encode(foley_encoder* e, const float* frames, int32_t n_frames, float* out, void* stream);
 /* "layers_run": stop after this many transformer layers (per-layer parity taps; -1 = all); "att_tc": 1 = tcgen05 / TMEM
  * self-attention kernel in the vision tower (default), 0 = the mma.sync flash kernel. */
 foley_status foley_encoder_set_option(foley_encoder* e, const char* key, int64_t value);

@@ -226,8 +226,8 @@ class _FakeTokenizer:
 
 
 def test_sampler_runs_frames_to_waveform_on_the_engine_encoders():
-    """Frames -> GPU preprocessing -> SigLIP2 on the engine + CLAP text on the engine (+ a stub for the borrowed Synchformer)
-    -> denoise -> DAC through HunyuanFoleySampler.generate_audio; the features the Sampler consumed equal the HF modules'
+    """Frames -> GPU preprocessing -> SigLIP2, Synchformer and CLAP text on the engine -> denoise -> DAC through
+    HunyuanFoleySampler.generate_audio (no torch module, no reference package anywhere on the path); the features the Sampler consumed equal the HF modules'
     on the same preprocessed frames / token ids within the bf16 floor."""
     nodes, cfgmod, E, enc, fb = (load_pkg(m) for m in ("nodes", "config", "engine", "encoders", "feature_bridge"))
     from oracle import weights as W
@@ -247,9 +247,12 @@ def test_sampler_runs_frames_to_waveform_on_the_engine_encoders():
     L, Lv, S = W.clip_lengths(1.0)
     seen = {}
 
+    from tools import synthetic as SY
+    sync = enc.SynchformerEncoder.from_state_dict(SY.synth_motionformer_state_dict(1, seed=5), **dict(enc.MOTIONFORMER_DIVIDED_224, num_layers=1))
+
     def sync_encode(frames):
         seen["sync_in"] = frames
-        return W.synth_conditions(c, L, Lv, S)["syncformer_feat"].cuda()
+        return sync.encode(frames[0])
 
     inner = fb.make_extract_features(sig, _FakeTokenizer(), clap, sync_encode, torch.device("cuda"))
 
@@ -266,6 +269,7 @@ def test_sampler_runs_frames_to_waveform_on_the_engine_encoders():
     assert batch["waveform"].shape == (1, 1, 48000) and torch.isfinite(batch["waveform"]).all()
     visual, text, audio_len = seen["out"]
     assert visual["siglip2_feat"].shape == (1, 8, 768) and seen["sync_in"].shape == (1, 25, 3, 224, 224) and audio_len == 1.0
+    assert visual["syncformer_feat"].shape == (1, 16, 768) and torch.isfinite(visual["syncformer_feat"]).all()
     tok = _FakeTokenizer()(["noisy", "rain on a tin roof"])
     assert text["uncond_text_feat"].shape == (1, tok["input_ids"].shape[1], 768) and text["text_feat"].shape == text["uncond_text_feat"].shape
     with torch.inference_mode():
@@ -273,3 +277,53 @@ def test_sampler_runs_frames_to_waveform_on_the_engine_encoders():
         want_txt = hf_clap.to(torch.bfloat16)(input_ids=tok["input_ids"].cuda(), attention_mask=tok["attention_mask"].cuda()).last_hidden_state
     assert rel_l2(visual["siglip2_feat"][0].float(), want_sig.float()) < 2e-2
     assert rel_l2(torch.cat([text["uncond_text_feat"], text["text_feat"]]).float(), want_txt.float()) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------- Synchformer (MotionFormer)
+@pytest.mark.parametrize("depth", [2, 12])
+def test_synchformer_vs_reference_golden(depth, golden_dir):
+    """The Synchformer visual extractor on the engine against the reference's OWN MotionFormer run on a B200
+    (tools/gpu_synchformer_golden.py: staged reference, bf16 parameters under fp16 autocast as the Sampler runs it —
+    feature_utils.py:100-102, nodes.py:283-284 — and the fp32 module as ground truth), same seeded weights and frames.
+    Tolerance: engine vs reference-autocast <= 2e-3 (measured 4.8e-4: same fp16 rounding points, other summation orders) and
+    engine vs fp32 <= 1.1 x (reference-autocast vs fp32, 7.4e-3)."""
+    import os
+    enc = load_pkg("encoders")
+    from tools import synthetic as SY
+    g = torch.load(os.path.join(golden_dir, f"synchformer_d{depth}.pt"))
+    frames = SY.synth_sync_frames(g["n_frames"], seed=g["frames_seed"]).cuda()
+    cfg = dict(enc.MOTIONFORMER_DIVIDED_224, num_layers=depth)
+    e = enc.SynchformerEncoder.from_state_dict(SY.synth_motionformer_state_dict(depth, seed=g["weights_seed"]), **cfg)
+    got = e.encode(frames)
+    torch.cuda.synchronize()
+    S = (g["n_frames"] - 16) // 8 + 1
+    assert got.shape == (1, S * 8, 768) and got.dtype == torch.float32 and torch.isfinite(got).all()
+    got = got[0].view(S, 8, 768).cpu()
+    d16, d32 = rel_l2(got, g["out_autocast"]), rel_l2(got, g["out_fp32"])
+    print(f"synchformer depth {depth}: engine vs reference autocast {d16:.3e}, vs fp32 {d32:.3e}, reference autocast vs fp32 {g['autocast_vs_fp32']:.3e}")
+    assert d16 <= 2e-3
+    assert d32 <= 1.1 * g["autocast_vs_fp32"]
+    assert all(f == 0 for f in _flags())
+    # Synchformer state-dict names (vfeat_extractor.*) with the audio extractor's tensors in between are accepted / ignored
+    sd = {"vfeat_extractor." + k: v for k, v in SY.synth_motionformer_state_dict(depth, seed=g["weights_seed"]).items()}
+    sd["afeat_extractor.ast.embeddings.cls_token"] = torch.zeros(1, 1, 768)
+    sd["transformer.pos_emb_cfg.pos_emb"] = torch.zeros(1, 8, 768)
+    e2 = enc.SynchformerEncoder.from_state_dict(sd, **cfg)
+    assert torch.equal(e2.encode(frames)[0].view(S, 8, 768).cpu(), got)
+    # windows are independent: a clip with one more window reproduces the first ones bit for bit
+    longer = SY.synth_sync_frames(g["n_frames"] + 8, seed=g["frames_seed"]).cuda()
+    longer[: g["n_frames"]] = frames
+    assert torch.equal(e.encode(longer)[0, : S * 8].cpu().view(S, 8, 768), got)
+
+
+def test_synchformer_refuses_short_clips_and_missing_weights():
+    enc, E = load_pkg("encoders"), load_pkg("engine")
+    from tools import synthetic as SY
+    cfg = dict(enc.MOTIONFORMER_DIVIDED_224, num_layers=1)
+    e = enc.SynchformerEncoder.from_state_dict(SY.synth_motionformer_state_dict(1), **cfg)
+    with pytest.raises(E.FoleyError, match="16 frames"):
+        e.encode(torch.zeros(15, 3, 224, 224))
+    sd = SY.synth_motionformer_state_dict(1)
+    del sd["blocks.0.timeattn.qkv.weight"]
+    with pytest.raises(E.FoleyError, match="missing tensor"):
+        enc.SynchformerEncoder.from_state_dict(sd, **cfg)

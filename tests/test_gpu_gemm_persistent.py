@@ -96,3 +96,24 @@ def test_swiglu_pairs():
     flags = (ctypes.c_uint32 * 4)()
     lib.foley_debug_flags(flags)
     assert flags[0] == 0
+
+
+@pytest.mark.parametrize("R,K,N,act,bn", [(21966, 768, 2304, 0, 256), (1569, 768, 3072, 4, 256), (112, 3072, 768, 0, 64), (300, 1536, 768, 0, 128)])
+def test_fp16_operands(R, K, N, act, bn):
+    """fp16 I/O mode (FOLEY_DT_F16: the Synchformer's Linear layers under fp16 autocast) on the persistent and the one-tile
+    kernel against fp32 matmul of the same fp16 operands rounded once to fp16 (tolerance: one fp16 rounding, 2^-11: 5e-4);
+    act 4 = nn.GELU()."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(R + N)
+    a = torch.randn(1, R, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    b = (torch.randn(N, device="cuda", generator=g) * 0.1).half()
+    out = torch.zeros(1, R, N, dtype=torch.float16, device="cuda")
+    st = lib.foley_gemm(a.data_ptr(), 2, 1, R, K, K, R * K, w.data_ptr(), N, 1, 0, 1, 1, bn, 0, act, b.data_ptr(), out.data_ptr(), N, R * N, R * N, None)
+    assert st == 0, lib.foley_last_error()
+    torch.cuda.synchronize()
+    want = (a[0].float() @ w.float().T + b.float()).half().float()
+    if act == 4:
+        want = torch.nn.functional.gelu(want).half().float()
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out[0].float(), want) < 5e-4

@@ -174,3 +174,73 @@ def load_reference():
     ns.FlowMatchDiscreteScheduler, ns.DAC, ns.utils = FlowMatchDiscreteScheduler, DAC, ref_utils
     ns.config_dir = os.path.join(REF_ROOT, "configs")
     return ns
+
+
+def install_synchformer_shims():
+    """omegaconf + timm stand-ins, enough for the reference's MotionFormer (models/synchformer/motionformer.py,
+    video_model_builder.py, vit_helper.py): OmegaConf.load of the committed divided_224_16x4.yaml into an attribute dict that
+    accepts assignment, timm.layers.{trunc_normal_, to_2tuple}."""
+    if "omegaconf" not in sys.modules:
+        import yaml
+
+        class _Node(dict):
+            def __getattr__(self, k):
+                try:
+                    return self[k]
+                except KeyError as e:
+                    raise AttributeError(k) from e
+
+            def __setattr__(self, k, v):
+                self[k] = v
+
+        def _wrap(o):
+            return _Node({k: _wrap(v) for k, v in o.items()}) if isinstance(o, dict) else o
+
+        oc = _mod("omegaconf")
+
+        class OmegaConf:
+            overrides = {}          # e.g. {"VIT.DEPTH": 2}: applied to every loaded config (small-depth goldens)
+
+            @staticmethod
+            def load(path):
+                with open(path) as f:
+                    cfg = _wrap(yaml.safe_load(f))
+                for k, v in OmegaConf.overrides.items():
+                    node = cfg
+                    parts = k.split(".")
+                    for q in parts[:-1]:
+                        node = node[q]
+                    node[parts[-1]] = v
+                return cfg
+
+        oc.OmegaConf = OmegaConf
+    try:
+        import timm  # noqa: F401
+    except Exception:   # noqa: BLE001
+        timm = _mod("timm")
+        layers = _mod("timm.layers")
+        layers.trunc_normal_ = torch.nn.init.trunc_normal_
+        layers.to_2tuple = lambda x: tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+        timm.layers = layers
+        tm = _mod("timm.models")
+        tml = _mod("timm.models.layers")
+        tml.trunc_normal_, tml.to_2tuple = layers.trunc_normal_, layers.to_2tuple
+        timm.models, tm.layers = tm, tml
+
+
+def load_motionformer(depth=None):
+    """The reference's MotionFormer class exactly as Synchformer.__init__ builds it (synchformer.py:21-27); `depth` overrides
+    VIT.DEPTH of its YAML (small-depth goldens)."""
+    install_synchformer_shims()
+    sys.modules["omegaconf"].OmegaConf.overrides = {"VIT.DEPTH": depth} if depth else {}
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    # import the sub-module without the package __init__ chain (utils/feature_utils pull av, loguru, ...)
+    pkg = "hunyuanvideo_foley.models.synchformer"
+    for name in ("hunyuanvideo_foley", "hunyuanvideo_foley.models", pkg):
+        if name not in sys.modules:
+            m = _mod(name)
+            m.__path__ = [os.path.join(REF_ROOT, *name.split("."))]
+    mf = importlib.import_module(pkg + ".motionformer")
+    return lambda: mf.MotionFormer(extract_features=True, factorize_space_time=True, agg_space_module="TransformerEncoderLayer",
+                                   agg_time_module="torch.nn.Identity", add_global_repr=False)

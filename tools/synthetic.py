@@ -228,3 +228,57 @@ def synth_state_dict_cuda(specs, seed, device, dtype):
             t = torch.randn(shape, generator=g, device=device, dtype=torch.float32) * scale[kind]
         out[name] = t.to(dtype)
     return out
+
+
+def motionformer_param_specs(depth=12, C=768, F=3072):
+    """State dict of the reference's MotionFormer as Synchformer.__init__ builds it (divided_224_16x4, spatial aggregation
+    layer; models/synchformer/motionformer.py, video_model_builder.py): (name, shape, kind) in module order."""
+    specs = [("cls_token", (1, 1, C), "e"), ("pos_embed", (1, 197, C), "e"), ("temp_embed", (1, 8, C), "e"),
+             ("patch_embed.proj.weight", (C, 3, 16, 16), "w"), ("patch_embed.proj.bias", (C,), "b"),
+             ("patch_embed_3d.proj.weight", (C, 3, 2, 16, 16), "w"), ("patch_embed_3d.proj.bias", (C,), "b")]
+    for i in range(depth):
+        p = f"blocks.{i}."
+        specs += [(p + "norm1.weight", (C,), "n"), (p + "norm1.bias", (C,), "b"),
+                  (p + "attn.qkv.weight", (3 * C, C), "w"), (p + "attn.qkv.bias", (3 * C,), "b"),
+                  (p + "attn.proj.weight", (C, C), "w"), (p + "attn.proj.bias", (C,), "b"),
+                  (p + "timeattn.qkv.weight", (3 * C, C), "w"), (p + "timeattn.qkv.bias", (3 * C,), "b"),
+                  (p + "timeattn.proj.weight", (C, C), "w"), (p + "timeattn.proj.bias", (C,), "b"),
+                  (p + "norm2.weight", (C,), "n"), (p + "norm2.bias", (C,), "b"),
+                  (p + "mlp.fc1.weight", (F, C), "w"), (p + "mlp.fc1.bias", (F,), "b"),
+                  (p + "mlp.fc2.weight", (C, F), "w"), (p + "mlp.fc2.bias", (C,), "b"),
+                  (p + "norm3.weight", (C,), "n"), (p + "norm3.bias", (C,), "b")]
+    a = "spatial_attn_agg."
+    specs += [("norm.weight", (C,), "n"), ("norm.bias", (C,), "b"), (a + "cls_token", (1, 1, C), "e"),
+              (a + "self_attn.in_proj_weight", (3 * C, C), "w"), (a + "self_attn.in_proj_bias", (3 * C,), "b"),
+              (a + "self_attn.out_proj.weight", (C, C), "w"), (a + "self_attn.out_proj.bias", (C,), "b"),
+              (a + "linear1.weight", (F, C), "w"), (a + "linear1.bias", (F,), "b"),
+              (a + "linear2.weight", (C, F), "w"), (a + "linear2.bias", (C,), "b"),
+              (a + "norm1.weight", (C,), "n"), (a + "norm1.bias", (C,), "b"),
+              (a + "norm2.weight", (C,), "n"), (a + "norm2.bias", (C,), "b")]
+    return specs
+
+
+def synth_motionformer_state_dict(depth=12, seed=0, dtype=torch.float32):
+    """Seeded MotionFormer weights (same values wherever they are drawn: CPU generator per tensor).  q/k/v projections get
+    1.5 x the fan-in scale so that the attention maps are far from uniform."""
+    sd = OrderedDict()
+    for name, shape, kind in motionformer_param_specs(depth):
+        t = _draw("mformer." + name, shape, kind, seed, torch.float32)
+        if "qkv.weight" in name or "in_proj_weight" in name:
+            t = t * 1.5
+        if kind == "e":
+            t = t * 0.2
+        sd[name] = t.to(dtype)
+    return sd
+
+
+def synth_sync_frames(n_frames, seed=0):
+    """Preprocessed 25 fps frames [n_frames, 3, 224, 224] in [-1, 1] with temporal structure (a drifting smooth pattern + noise)."""
+    g = torch.Generator(device="cpu").manual_seed(1000 + seed)
+    base = torch.rand(3, 28, 28, generator=g)
+    fr = []
+    for t in range(n_frames):
+        img = torch.roll(base, shifts=(t // 2, t // 3), dims=(1, 2))
+        img = torch.nn.functional.interpolate(img[None], size=(224, 224), mode="bilinear", align_corners=False)[0]
+        fr.append((img + 0.1 * torch.rand(3, 224, 224, generator=g)).clamp(0, 1) * 2 - 1)
+    return torch.stack(fr)
