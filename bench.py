@@ -617,9 +617,33 @@ def condition_encoders(args, dev):
                                 "ms_hf_eager_bf16": timed(lambda: clap(input_ids=idc, attention_mask=mc).last_hidden_state),
                                 "rel_l2_vs_hf_bf16": float((got - want).norm() / want.norm())}
             del clap, e_clap
+            # Synchformer visual extractor: 25 fps frames of the clip; the reference's own module (staged tree) when available
+            T25 = int(args.duration * 25)
+            frames = SY.synth_sync_frames(min(T25, 64), seed=0).to(dev)
+            frames = frames.repeat((T25 + frames.shape[0] - 1) // frames.shape[0], 1, 1, 1)[:T25].contiguous()
+            sd = SY.synth_motionformer_state_dict(12, seed=0)
+            e_sync = enc.SynchformerEncoder.from_state_dict(sd, device=dev)
+            got = e_sync.encode(frames)
+            out["synchformer"] = {"frames": T25, "segments": got.shape[1] // 8, "ms": timed(lambda: e_sync.encode(frames))}
+            try:
+                from tools import ref_shims as R
+                ref = R.load_motionformer(12)().eval()
+                ref.load_state_dict(sd, strict=True)
+                ref = ref.to(dev).to(torch.bfloat16)
+                S = got.shape[1] // 8
+                x = torch.stack([frames[i * 8: i * 8 + 16] for i in range(S)])[None].permute(0, 1, 3, 2, 4, 5)
+                with torch.autocast(device_type="cuda", enabled=True, dtype=torch.half):
+                    want = ref(x).float().reshape(1, S * 8, -1)
+                    out["synchformer"]["ms_reference_eager_fp16_autocast"] = timed(lambda: ref(x), 3)
+                out["synchformer"]["rel_l2_vs_reference_autocast"] = float((got - want).norm() / want.norm())
+                del ref
+            except Exception as e:   # noqa: BLE001 — no staged reference tree on this box
+                out["synchformer"]["reference"] = "unavailable: " + repr(e)[:120]
+            del e_sync
         torch.cuda.empty_cache()
-        out["what"] = ("SigLIP2-base-patch16-512 vision tower + pooling head and CLAP text tower (seeded random weights) on the engine vs the HF "
-                       "modules in bf16, eager, same GPU; Synchformer is not built (DESIGN.md §8)")
+        out["what"] = ("SigLIP2-base-patch16-512 vision tower + pooling head and CLAP text tower on the engine vs the HF modules in bf16, "
+                       "Synchformer visual extractor on the engine vs the reference's own module under fp16 autocast; eager, same GPU, "
+                       "seeded random weights")
         return out
     except Exception as e:   # noqa: BLE001
         return {"unavailable": repr(e)}

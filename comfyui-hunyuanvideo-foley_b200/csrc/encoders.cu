@@ -471,8 +471,19 @@ foley_status Encoder::sync_ln(cudaStream_t st, SyncLnArgs a) {
     return FOLEY_OK;
 }
 
+// One query per (sample, head): the block-per-unit kernel (the one-warp kernel walked 1569 keys serially: 263 us per call).
+template <bool kHalf>
+static foley_status launch_cls_attention(const EncAttnArgs& a, cudaStream_t st) {
+    const size_t smem = (static_cast<size_t>((a.Sk + 3) & ~3) + ECA_WARPS * 64) * sizeof(float);
+    if (smem > 48 * 1024) return fail(FOLEY_ERR_UNSUPPORTED, "class-token attention: too many keys");
+    FOLEY_CUDA_OK(launch_k(enc_cls_attention_kernel<kHalf>, dim3(static_cast<unsigned>(a.B) * a.H), dim3(32 * ECA_WARPS), smem, st, a));
+    return FOLEY_OK;
+}
+
 foley_status Encoder::attention(cudaStream_t st, const EncAttnArgs& a, bool small) {
-    if (small) {
+    if (small && a.Sq == 1) {
+        ST_OK(launch_cls_attention<false>(a, st));
+    } else if (small) {
         const size_t smem = static_cast<size_t>(ESA_WARPS) * a.Sk * sizeof(float);
         if (smem > 64 * 1024) return fail(FOLEY_ERR_UNSUPPORTED, "small attention: too many keys");
         const long long units = static_cast<long long>(a.B) * a.H * a.Sq;
@@ -661,8 +672,7 @@ foley_status Encoder::synchformer_encode(const float* frames, int n_frames, floa
             ca.q_row_stride = ca.kv_row_stride = 3LL * C; ca.q_batch_stride = ca.kv_batch_stride = 3LL * C * NTOK;
             ca.o_row_stride = C; ca.o_batch_stride = static_cast<long long>(C) * NTOK;
             ca.scale = 0.125f; ca.round_scores = 1;
-            const size_t smem = static_cast<size_t>(ESA_WARPS) * ca.Sk * sizeof(float);
-            FOLEY_CUDA_OK(launch_k(enc_small_attention_kernel<true>, dim3(enc_blocks(static_cast<long long>(Sc) * H, ESA_WARPS)), dim3(32 * ESA_WARPS), smem, st, ca));
+            ST_OK(launch_cls_attention<true>(ca, st));
             ++launches;
             return FOLEY_OK;
         };
@@ -730,8 +740,7 @@ foley_status Encoder::synchformer_encode(const float* frames, int n_frames, floa
             ca.q_row_stride = ca.kv_row_stride = 3LL * C; ca.q_batch_stride = ca.kv_batch_stride = 3LL * C * SEQ;
             ca.o_row_stride = C; ca.o_batch_stride = C;
             ca.scale = 0.125f;
-            const size_t smem = static_cast<size_t>(ESA_WARPS) * ca.Sk * sizeof(float);
-            FOLEY_CUDA_OK(launch_k(enc_small_attention_kernel<true>, dim3(enc_blocks(nseq * H, ESA_WARPS)), dim3(32 * ESA_WARPS), smem, st, ca));
+            ST_OK(launch_cls_attention<true>(ca, st));
             ++launches;
         }
         ST_OK(gemm(st, att, nseq, s_out_proj, y, ACT_NONE, 1));
@@ -868,14 +877,15 @@ extern "C" foley_status foley_encoder_debug_read(foley_encoder* e, const char* w
 }
 
 // softmax(Q K^T * scale) V for head_dim 64, exported for unit tests.  impl 0: flash kernel (no mask); impl 1: one warp per
-// query row (key mask, optional bf16 rounding of scores); impl 2: tcgen05 / TMEM kernel (no mask).
+// query row (key mask, optional bf16 rounding of scores); impl 2: tcgen05 / TMEM kernel (no mask); impl 3: one CTA per
+// (sample, head) for a single query over many keys (class-token / pooling-probe queries).
 extern "C" foley_status foley_attention_d64(const void* q, const void* k, const void* v, void* out, int32_t batch, int32_t heads,
                                             int32_t Sq, int32_t Sk, int64_t q_batch_stride, int64_t q_row_stride,
                                             int64_t kv_batch_stride, int64_t kv_row_stride, int64_t o_batch_stride,
                                             int64_t o_row_stride, float scale, const int32_t* key_mask, int32_t round_scores,
                                             int32_t impl, void* stream) {
     if (!q || !k || !v || !out || batch < 1 || heads < 1 || Sq < 1 || Sk < 1) return fail(FOLEY_ERR_INVALID, "foley_attention_d64: bad argument");
-    if (impl != 1 && (key_mask || round_scores)) return fail(FOLEY_ERR_UNSUPPORTED, "foley_attention_d64: the flash kernels take no mask");
+    if (impl != 1 && impl != 3 && (key_mask || round_scores)) return fail(FOLEY_ERR_UNSUPPORTED, "foley_attention_d64: the flash kernels take no mask");
     EncAttnArgs a;
     a.q = static_cast<const bf16*>(q); a.k = static_cast<const bf16*>(k); a.v = static_cast<const bf16*>(v); a.o = static_cast<bf16*>(out);
     a.B = batch; a.H = heads; a.Sq = Sq; a.Sk = Sk;
@@ -897,6 +907,10 @@ extern "C" foley_status foley_attention_d64(const void* q, const void* k, const 
         if (!launch_attention_tc64(a.q, a.k, a.v, q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride, batch, t, st, &err))
             return fail(FOLEY_ERR_CUDA, err);
         return FOLEY_OK;
+    }
+    if (impl == 3) {
+        if (Sq != 1) return fail(FOLEY_ERR_INVALID, "foley_attention_d64: impl 3 is the one-query kernel");
+        return launch_cls_attention<false>(a, st);
     }
     if (impl == 1) {
         const size_t smem = static_cast<size_t>(ESA_WARPS) * Sk * sizeof(float);

@@ -464,6 +464,103 @@ __global__ void __launch_bounds__(32 * ESA_WARPS) enc_small_attention_kernel(con
     *reinterpret_cast<uint32_t*>(O) = kHalf ? pack_f16x2(acc0, acc1) : pack_bf16x2(acc0, acc1);
 }
 
+// ONE query per (sample, head) over many keys (the class-token queries of the Synchformer: 1569 keys; the SigLIP pooling probe:
+// 1024 keys): one CTA of 8 warps per (sample, head).  Phase 1: a thread owns whole keys (64-channel dot products), scores
+// (rounded to the operand type when round_scores) into shared memory, block-wide maximum and sum; phase 2: warp w takes the w-th
+// slice of the keys, a lane owns two channels, P = round(p / sum) exactly as the one-warp kernel; the 8 partial outputs are
+// summed through shared memory.  Same arithmetic as enc_small_attention_kernel (the summation order over keys differs).
+constexpr int ECA_WARPS = 8;
+template <bool kHalf>
+__global__ void __launch_bounds__(32 * ECA_WARPS) enc_cls_attention_kernel(const EncAttnArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ float eca_smem[];
+    float* sc = eca_smem;                          // [Sk]
+    float* red = eca_smem + ((a.Sk + 3) & ~3);     // [ECA_WARPS][64] partial outputs; first 2 * ECA_WARPS floats double as reduction slots
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x % a.H, b = blockIdx.x / a.H;
+    const __nv_bfloat16* Q = a.q + b * a.q_batch_stride + h * EA_D;
+    const __nv_bfloat16* K = a.k + b * a.kv_batch_stride + h * EA_D;
+    const __nv_bfloat16* V = a.v + b * a.kv_batch_stride + h * EA_D;
+    float qv[EA_D];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float f[8];
+        if constexpr (kHalf) unpack8h(*reinterpret_cast<const uint4*>(Q + c * 8), f);
+        else unpack8(*reinterpret_cast<const uint4*>(Q + c * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qv[c * 8 + j] = f[j];
+    }
+    float mx = -INFINITY;
+    for (int key = threadIdx.x; key < a.Sk; key += 32 * ECA_WARPS) {
+        const __nv_bfloat16* kr = K + key * a.kv_row_stride;
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float f[8];
+            if constexpr (kHalf) unpack8h(*reinterpret_cast<const uint4*>(kr + c * 8), f);
+            else unpack8(*reinterpret_cast<const uint4*>(kr + c * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dot = fmaf(qv[c * 8 + j], f[j], dot);
+        }
+        float sv = dot * a.scale;
+        if (a.round_scores) sv = kHalf ? f16_round(sv) : bf16_round(sv);
+        if (a.key_mask && a.key_mask[static_cast<long long>(b) * a.Sk + key] == 0) sv = -INFINITY;
+        sc[key] = sv;
+        mx = fmaxf(mx, sv);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < ECA_WARPS; ++w) mx = fmaxf(mx, red[w]);
+    float sum = 0.f;
+    for (int key = threadIdx.x; key < a.Sk; key += 32 * ECA_WARPS) {
+        const float p = __expf(sc[key] - mx);
+        sc[key] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[ECA_WARPS + warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < ECA_WARPS; ++w) sum += red[ECA_WARPS + w];
+    const float inv = 1.0f / sum;
+    __syncthreads();                                // the reduction slots are about to hold partial outputs
+    const int per = (a.Sk + ECA_WARPS - 1) / ECA_WARPS;
+    const int k0 = warp * per, k1 = min(a.Sk, k0 + per);
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    const __nv_bfloat16* vp = V + lane * 2;
+    auto term = [&](int key, float& x0, float& x1) {
+        if constexpr (kHalf) {
+            const float p = f16_round(sc[key] * inv);
+            const __half2 v2 = *reinterpret_cast<const __half2*>(vp + key * a.kv_row_stride);
+            x0 = fmaf(p, __low2float(v2), x0);
+            x1 = fmaf(p, __high2float(v2), x1);
+        } else {
+            const float p = bf16_round(sc[key] * inv);
+            const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(vp + key * a.kv_row_stride);
+            x0 = fmaf(p, __low2float(v2), x0);
+            x1 = fmaf(p, __high2float(v2), x1);
+        }
+    };
+    int key = k0;
+    for (; key + 1 < k1; key += 2) { term(key, acc0, acc1); term(key + 1, acc2, acc3); }
+    if (key < k1) term(key, acc0, acc1);
+    red[warp * 64 + lane * 2] = acc0 + acc2;
+    red[warp * 64 + lane * 2 + 1] = acc1 + acc3;
+    __syncthreads();
+    if (warp == 0) {
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < ECA_WARPS; ++w) { o0 += red[w * 64 + lane * 2]; o1 += red[w * 64 + lane * 2 + 1]; }
+        __nv_bfloat16* O = a.o + b * a.o_batch_stride + h * EA_D + lane * 2;
+        *reinterpret_cast<uint32_t*>(O) = kHalf ? pack_f16x2(o0, o1) : pack_bf16x2(o0, o1);
+    }
+}
+
 // ================================================================================================ Synchformer (MotionFormer)
 // The reference runs its Synchformer visual extractor under torch.autocast(fp16) on a module whose parameters were moved to
 // the DiT's dtype (feature_utils.py:100-102, nodes.py:283-284): Linear / Conv3d / einsum in fp16 (fp32 accumulation), LayerNorm

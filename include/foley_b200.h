@@ -301,7 +301,8 @@ foley_status foley_encoder_debug_read(foley_encoder* e, const char* what, float*
 /* softmax(Q K^T * scale) V for head_dim 64 (HF SiglipAttention / ClapTextSelfAttention / nn.MultiheadAttention of the
  * pooling head).  Element (b, h, r, d) of an operand at ptr + b*batch_stride + r*row_stride + h*64 + d (bf16, device).
  * impl 0: flash-style mma.sync kernel, no mask; impl 2: tcgen05 / TMEM kernel, no mask (the vision tower's default); impl 1: one warp per query row, key_mask = DEVICE int32 [batch, Sk] (0 = padded
- * key) and optional bf16 rounding of scores and probabilities (the bmm + softmax path of nn.MultiheadAttention). */
+ * key) and optional bf16 rounding of scores and probabilities (the bmm + softmax path of nn.MultiheadAttention); impl 3: the
+ * same arithmetic for ONE query per (sample, head) over many keys, one CTA per unit (pooling probe, class-token queries). */
 foley_status foley_attention_d64(const void* q, const void* k, const void* v, void* out, int32_t batch, int32_t heads,
                                  int32_t Sq, int32_t Sk, int64_t q_batch_stride, int64_t q_row_stride,
                                  int64_t kv_batch_stride, int64_t kv_row_stride, int64_t o_batch_stride,

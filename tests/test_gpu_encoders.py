@@ -43,7 +43,8 @@ def _ref_attn64(q, k, v, H, mask=None):
 @pytest.mark.parametrize("name,B,H,Sq,Sk,impl", [
     ("siglip_frame", 2, 12, 1024, 1024, 0), ("ragged", 2, 3, 130, 77, 0), ("one_tile", 1, 2, 64, 64, 0),
     ("tiny", 1, 1, 5, 3, 0), ("tc_siglip_frame", 2, 12, 1024, 1024, 2), ("tc_ragged", 2, 3, 130, 77, 2), ("tc_one_chunk", 1, 2, 128, 128, 2),
-    ("tc_tiny", 1, 1, 5, 3, 0 + 2), ("tc_odd_chunks", 1, 2, 300, 333, 2), ("tc_many_ctas", 5, 12, 1024, 1024, 2), ("clap", 2, 12, 77, 77, 1), ("clap_long", 1, 12, 300, 300, 1), ("pool", 3, 12, 1, 1024, 1)])
+    ("tc_tiny", 1, 1, 5, 3, 0 + 2), ("tc_odd_chunks", 1, 2, 300, 333, 2), ("tc_many_ctas", 5, 12, 1024, 1024, 2), ("clap", 2, 12, 77, 77, 1), ("clap_long", 1, 12, 300, 300, 1), ("pool", 3, 12, 1, 1024, 1),
+    ("pool_blk", 3, 12, 1, 1024, 3), ("cls_blk", 2, 12, 1, 1569, 3), ("clap_blk_masked", 2, 3, 1, 77, 3)])
 def test_attention_d64_vs_fp32(name, B, H, Sq, Sk, impl):
     enc = load_pkg("encoders")
     g = torch.Generator(device="cuda").manual_seed(len(name) * 7 + Sq)
@@ -56,7 +57,7 @@ def test_attention_d64_vs_fp32(name, B, H, Sq, Sk, impl):
         kv = torch.randn(B, Sk, 2 * C, device="cuda", generator=g).bfloat16()
         k, v = kv[..., :C], kv[..., C:]
     mask = None
-    if impl == 1 and name.startswith("clap"):
+    if impl in (1, 3) and name.startswith("clap"):
         mask = torch.ones(B, Sk, dtype=torch.int32, device="cuda")
         mask[0, Sk - Sk // 3:] = 0
     out = enc.attention_d64(q, k, v, H, key_mask=mask, impl=impl)
@@ -91,8 +92,9 @@ def test_pool_attention_rounds_like_multihead_attention():
         k = torch.nn.functional.linear(xs, Wk, bk)
         v = torch.nn.functional.linear(xs, Wv, bv)
         want = mha(probe.expand(B, 1, C), xs, xs)[0]
-        got = torch.nn.functional.linear(enc.attention_d64(q, k, v, H, round_scores=True, impl=1), mha.out_proj.weight, mha.out_proj.bias)
-    assert rel_l2(got.float(), want.float()) < 4e-3
+        for impl in (1, 3):
+            got = torch.nn.functional.linear(enc.attention_d64(q, k, v, H, round_scores=True, impl=impl), mha.out_proj.weight, mha.out_proj.bias)
+            assert rel_l2(got.float(), want.float()) < 4e-3, impl
 
 
 def _siglip(layers, image, seed):

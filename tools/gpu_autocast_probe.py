@@ -1,7 +1,8 @@
-"""Does the reference's Synchformer call (feature_utils.py:100-102: fp16 autocast around a module that the Sampler has
-moved to the DiT's dtype, nodes.py:283-284) run at all when that dtype is bf16?  The MotionFormer concatenates its bf16 class
-token with the fp16 patch embeddings (video_model_builder.py forward_features: torch.cat((cls_tokens, x), dim=1)) under
-autocast; `cat` is an autocast "promote" op.  Prints one JSON line."""
+"""Which types does the reference's Synchformer call produce (feature_utils.py:100-102: fp16 autocast around a module that the
+Sampler has moved to the DiT's dtype, nodes.py:283-284)?  The MotionFormer concatenates its class token (module dtype) with
+the patch embeddings (fp16 under autocast) — video_model_builder.py forward_features: torch.cat((cls_tokens, x), dim=1); `cat`
+is an autocast "promote" op.  Measured on the B200: bf16 module -> conv fp16, concatenation fp32 (the residual stream is fp32
+from there on); fp16 module -> fp16.  Prints one JSON line (profiles/r02_autocast_probe.json)."""
 import json
 
 import torch
