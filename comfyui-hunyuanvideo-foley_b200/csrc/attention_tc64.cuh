@@ -26,20 +26,30 @@ struct AttTc64Args {
     float scale_log2 = 0.f;                // softmax scale * log2(e)
 };
 
-constexpr int A64_THREADS = 160;
+constexpr int A64_THREADS = 160;                          // HALVES = 1: 4 row warps + the control warp (HALVES = 2: 288)
 constexpr int A64_CK = 128;                               // keys per chunk
 constexpr int A64_TILE = 128 * 128;                       // a [128 rows x 64 channels] bf16 tile: 16 KB
 constexpr int A64_OFF_K = A64_TILE;                       // Q | K0 K1 | V0 V1 | P (two 64-key blocks) | barriers
 constexpr int A64_OFF_V = A64_OFF_K + 2 * A64_TILE;
 constexpr int A64_OFF_P = A64_OFF_V + 2 * A64_TILE;
 constexpr int A64_OFF_BAR = A64_OFF_P + 2 * A64_TILE;
-constexpr int A64_SMEM = A64_OFF_BAR + 128;               // 114816 bytes: two CTAs per SM
+constexpr int A64_OFF_MX = A64_OFF_BAR + 128;             // HALVES = 2: [2][128] bf16 row-maximum exchange between the two column halves
+constexpr int A64_SMEM = A64_OFF_MX + 512;                // 115328 bytes: two CTAs per SM (limit 115712)
 constexpr int A64_O_COL = 128;                            // TMEM: S columns [0, 128), O columns [128, 192)
 constexpr int A64_O_PITCH = 144;                          // output staging: 128 B per row + 16 B (conflict-free)
 
-__global__ void __launch_bounds__(A64_THREADS, 2)
+// HALVES = 2: TWO threads per query row (warps w and w + 4 share a TMEM lane quarter and split the 128 columns of an S chunk
+// and the 64 channels of O): 8 row warps per CTA, four per scheduler with two CTAs per SM, so that one warp's exponentials
+// run under another's tcgen05.ld / maximum / P stores (HALVES = 1 left the MUFU unit ~42 % busy: ncu, profiles/).  The two
+// threads of a row agree on the running maximum through a bf16 value rounded UP (any common upper bound is a valid softmax
+// shift) exchanged in shared memory behind a 64-thread named barrier.
+template <int HALVES>
+__global__ void __launch_bounds__(32 * (4 * HALVES + 1), 2)
 attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const AttTc64Args a) {
+    constexpr int THREADS = 32 * (4 * HALVES + 1), ROW_THREADS = 128 * HALVES, CTRL_WARP = 4 * HALVES;
+    constexpr int NG = 4 / HALVES;                            // 32-column groups of an S chunk per thread
+    constexpr int OC = 64 / HALVES;                           // O channels per thread
     extern __shared__ __align__(1024) uint8_t a64_smem[];
     const uint32_t sQ = smem_u32(a64_smem);
     const uint32_t sK = sQ + A64_OFF_K, sV = sQ + A64_OFF_V, sP = sQ + A64_OFF_P;
@@ -58,14 +68,14 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
     if ((sQ & 1023u) != 0) { if (threadIdx.x == 0) atomicCAS(&g_foley_dbg[0], 0u, 0x7a0u); return; }   // layout assumption of the descriptors
     if (warp == 0) tmem_alloc<256>(tmem_slot);
-    if (threadIdx.x == 128) {
+    if (threadIdx.x == ROW_THREADS) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_k);
         tma_prefetch_desc(&tm_v);
         for (int i = 0; i < 2; ++i) { mbar_init(&full_k[i], 1); mbar_init(&full_v[i], 1); }
         mbar_init(bar_s, 1);
         mbar_init(bar_o, 1);
-        mbar_init(p_ready, 128);
+        mbar_init(p_ready, ROW_THREADS);
         fence_barrier_init();
     }
     tc_fence_before();
@@ -75,7 +85,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     pdl_wait();
     pdl_trigger();
 
-    if (warp == 4) {
+    if (warp == CTRL_WARP) {
         // ================================================================== control lane: TMA copies and MMAs
         if (lane == 0) {
             auto issue_k = [&](int c) {
@@ -128,18 +138,20 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
         __syncwarp();
     } else {
-        // ================================================================== 4 row warps: softmax + O accumulation
-        const int row = warp * 32 + lane;                       // query row of the tile = TMEM lane
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-        float o_acc[64];
+        // ================================================================== row warps: softmax + O accumulation
+        const int q = warp & 3, hf = warp >> 2;                 // TMEM lane quarter; which half of the columns (HALVES = 2)
+        const int row = q * 32 + lane;                          // query row of the tile = TMEM lane
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        __nv_bfloat16* mxs = reinterpret_cast<__nv_bfloat16*>(a64_smem + A64_OFF_MX);
+        float o_acc[OC];
 #pragma unroll
-        for (int j = 0; j < 64; ++j) o_acc[j] = 0.f;
+        for (int j = 0; j < OC; ++j) o_acc[j] = 0.f;
         float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
-        auto take_o = [&](float corr) {                          // o_acc = o_acc * corr + O chunk
+        auto take_o = [&](float corr) {                          // o_acc = o_acc * corr + this thread's channels of the O chunk
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
+            for (int g = 0; g < OC / 32; ++g) {
                 uint32_t ov[32];
-                tmem_ld_32x32(t_row + A64_O_COL + g * 32, ov);
+                tmem_ld_32x32(t_row + A64_O_COL + hf * OC + g * 32, ov);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) o_acc[g * 32 + j] = fmaf(o_acc[g * 32 + j], corr, __uint_as_float(ov[j]));
@@ -150,9 +162,12 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             const int n_grp = (kn + 31) >> 5;
             mbar_wait(bar_s, c & 1, 0x700 + (c & 15));
             tc_fence_after();
-            // ---- pass 1: row maximum
+            // ---- pass 1: row maximum over this thread's column groups
             float mx = -INFINITY;
-            for (int g = 0; g < n_grp; ++g) {
+#pragma unroll 1
+            for (int gi = 0; gi < NG; ++gi) {
+                const int g = hf * NG + gi;
+                if (g >= n_grp) break;
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + g * 32, v);
                 tmem_ld_wait();
@@ -164,7 +179,18 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                     for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (g * 32 + j) < kn ? __uint_as_float(v[j]) : -INFINITY);
                 }
             }
-            const float m_new = fmaxf(m_run, mx * a.scale_log2);
+            float m_new;
+            if constexpr (HALVES == 2) {
+                // both threads of the row use max(up(own), up(partner)): identical on both sides, >= the true maximum.
+                // (single-buffered: a thread writes its next value only after bar_s(c+1), i.e. after every row thread has
+                //  arrived on p_ready(c), which comes after this read)
+                const __nv_bfloat16 up = __float2bfloat16_ru(mx * a.scale_log2);
+                mxs[hf * 128 + row] = up;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                m_new = fmaxf(m_run, fmaxf(__bfloat162float(up), __bfloat162float(mxs[(1 - hf) * 128 + row])));
+            } else {
+                m_new = fmaxf(m_run, mx * a.scale_log2);
+            }
             const float corr = ex2_fast(m_run - m_new);         // first chunk: ex2(-inf) = 0
             m_run = m_new;
             // ---- O(c-1): PV(c-1) ran under pass 1; its completion also frees the P buffer
@@ -176,7 +202,10 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             corr_prev = corr;
             // ---- pass 2: exponentials -> bf16 P (K-major swizzled A operand), row sum from the fp32 values
             float l_chunk = 0.f;
-            for (int g = 0; g < n_grp; ++g) {
+#pragma unroll 1
+            for (int gi = 0; gi < NG; ++gi) {
+                const int g = hf * NG + gi;
+                if (g >= n_grp) break;
                 uint32_t v[32], pk[16];
                 tmem_ld_32x32(t_row + g * 32, v);
                 tmem_ld_wait();
@@ -192,10 +221,16 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         mbar_wait(bar_o, (n_chunks - 1) & 1, 0x760);
         tc_fence_after();
         take_o(corr_prev);
+        if constexpr (HALVES == 2) {    // the row sum is the sum of the two halves' sums (same maximum sequence); P is dead by now
+            float* ls = reinterpret_cast<float*>(a64_smem + A64_OFF_P);
+            ls[hf * 128 + row] = l_run;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            l_run += ls[(1 - hf) * 128 + row];
+        }
         const float inv = __fdividef(1.0f, l_run);
-        const uint32_t dst = sQ + static_cast<uint32_t>(row) * A64_O_PITCH;
+        const uint32_t dst = sQ + static_cast<uint32_t>(row) * A64_O_PITCH + static_cast<uint32_t>(hf * OC * 2);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < OC / 8; ++j)
             st_shared_v4(dst + j * 16, pack_bf16x2(o_acc[8 * j] * inv, o_acc[8 * j + 1] * inv),
                          pack_bf16x2(o_acc[8 * j + 2] * inv, o_acc[8 * j + 3] * inv),
                          pack_bf16x2(o_acc[8 * j + 4] * inv, o_acc[8 * j + 5] * inv),
@@ -205,7 +240,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     __syncthreads();                                            // staged tile complete; every MMA has completed
     {   // whole 128-byte row segments to global: 8 lanes per row
         __nv_bfloat16* O = a.o + b * a.o_batch_stride + h * 64;
-        for (int piece = threadIdx.x; piece < 128 * 8; piece += A64_THREADS) {
+        for (int piece = threadIdx.x; piece < 128 * 8; piece += THREADS) {
             const int r = piece >> 3, pc = piece & 7;
             if (q0 + r < a.Sq) {
                 const uint4 u = ld_shared_v4(sQ + static_cast<uint32_t>(r) * A64_O_PITCH + static_cast<uint32_t>(pc) * 16u);
@@ -250,13 +285,15 @@ inline bool encode_att64_map(CUtensorMap* out, const __nv_bfloat16* ptr, long lo
 }
 
 inline cudaError_t attention_tc64_init() {
-    return cudaFuncSetAttribute(attention_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A64_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, A64_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(attention_tc64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, A64_SMEM);
 }
 
 // q / k / v: (b, r, h, d) operands with their own row / batch strides (elements); heads are 64 channels apart.
 inline bool launch_attention_tc64(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, long long q_row_stride,
                                   long long q_batch_stride, long long kv_row_stride, long long kv_batch_stride, int batch,
-                                  const AttTc64Args& a, cudaStream_t st, std::string* err) {
+                                  const AttTc64Args& a, cudaStream_t st, std::string* err, int halves = 2) {
     CUtensorMap mq, mk, mv;
     if (!encode_att64_map(&mq, q, a.Sq, a.H, batch, q_row_stride, q_batch_stride, err) ||
         !encode_att64_map(&mk, k, a.Sk, a.H, batch, kv_row_stride, kv_batch_stride, err) ||
@@ -264,7 +301,7 @@ inline bool launch_attention_tc64(const __nv_bfloat16* q, const __nv_bfloat16* k
         return false;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>((a.Sq + 127) / 128), static_cast<unsigned>(a.H), static_cast<unsigned>(batch));
-    cfg.blockDim = dim3(A64_THREADS);
+    cfg.blockDim = dim3(halves == 2 ? 288 : A64_THREADS);
     cfg.dynamicSmemBytes = A64_SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -272,7 +309,8 @@ inline bool launch_attention_tc64(const __nv_bfloat16* q, const __nv_bfloat16* k
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, attention_tc64_kernel, mq, mk, mv, a);
+    const cudaError_t e = halves == 2 ? cudaLaunchKernelEx(&cfg, attention_tc64_kernel<2>, mq, mk, mv, a)
+                                      : cudaLaunchKernelEx(&cfg, attention_tc64_kernel<1>, mq, mk, mv, a);
     if (e != cudaSuccess) {
         if (err) *err = std::string("attention (d64) launch failed: ") + cudaGetErrorString(e);
         return false;

@@ -38,8 +38,9 @@ class Encoder {
     int device = 0, num_sms = 148;
     int C = 0, H = 0, NL = 0, F = 0;
     bool finalized = false;
-    int att_tc = 1;                        // self-attention of the vision tower: 1 = tcgen05 / TMEM kernel (attention_tc64.cuh), 0 = the
-                                           // mma.sync flash kernel (FOLEY_ENC_ATT_TC=0; option "att_tc")
+    int att_tc = 1;                        // self-attention of the vision tower: 1 = tcgen05 / TMEM kernel (attention_tc64.cuh) with two threads
+                                           // per query row, 2 = the same with one thread per row, 0 = the mma.sync flash kernel
+                                           // (FOLEY_ENC_ATT_TC; option "att_tc")
     int layers_run = -1;                   // option "layers_run": stop after this many layers (per-layer parity taps); -1 = all
     int64_t launches = 0;
     std::unordered_map<std::string, RawTensor> raw;
@@ -493,7 +494,8 @@ foley_status Encoder::attention(cudaStream_t st, const EncAttnArgs& a, bool smal
         t.o = a.o; t.o_batch_stride = a.o_batch_stride; t.o_row_stride = a.o_row_stride; t.H = a.H; t.Sq = a.Sq; t.Sk = a.Sk;
         t.scale_log2 = a.scale * 1.4426950408889634f;
         std::string err;
-        if (!launch_attention_tc64(a.q, a.k, a.v, a.q_row_stride, a.q_batch_stride, a.kv_row_stride, a.kv_batch_stride, a.B, t, st, &err))
+        if (!launch_attention_tc64(a.q, a.k, a.v, a.q_row_stride, a.q_batch_stride, a.kv_row_stride, a.kv_batch_stride, a.B, t, st, &err,
+                                   att_tc == 1 ? 2 : 1))
             return fail(FOLEY_ERR_CUDA, err);
     } else {
         dim3 grid((a.Sq + EA_BM - 1) / EA_BM, a.H, a.B);
@@ -899,12 +901,13 @@ extern "C" foley_status foley_attention_d64(const void* q, const void* k, const 
         FOLEY_CUDA_OK(attention_tc64_init());
         attr = true;
     }
-    if (impl == 2) {
+    if (impl == 2 || impl == 4) {         // 2: two threads per query row (default), 4: one thread per row
         AttTc64Args t;
         t.o = a.o; t.o_batch_stride = o_batch_stride; t.o_row_stride = o_row_stride; t.H = heads; t.Sq = Sq; t.Sk = Sk;
         t.scale_log2 = scale * 1.4426950408889634f;
         std::string err;
-        if (!launch_attention_tc64(a.q, a.k, a.v, q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride, batch, t, st, &err))
+        if (!launch_attention_tc64(a.q, a.k, a.v, q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride, batch, t, st, &err,
+                                   impl == 2 ? 2 : 1))
             return fail(FOLEY_ERR_CUDA, err);
         return FOLEY_OK;
     }

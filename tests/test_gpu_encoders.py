@@ -43,7 +43,8 @@ def _ref_attn64(q, k, v, H, mask=None):
 @pytest.mark.parametrize("name,B,H,Sq,Sk,impl", [
     ("siglip_frame", 2, 12, 1024, 1024, 0), ("ragged", 2, 3, 130, 77, 0), ("one_tile", 1, 2, 64, 64, 0),
     ("tiny", 1, 1, 5, 3, 0), ("tc_siglip_frame", 2, 12, 1024, 1024, 2), ("tc_ragged", 2, 3, 130, 77, 2), ("tc_one_chunk", 1, 2, 128, 128, 2),
-    ("tc_tiny", 1, 1, 5, 3, 0 + 2), ("tc_odd_chunks", 1, 2, 300, 333, 2), ("tc_many_ctas", 5, 12, 1024, 1024, 2), ("clap", 2, 12, 77, 77, 1), ("clap_long", 1, 12, 300, 300, 1), ("pool", 3, 12, 1, 1024, 1),
+    ("tc_tiny", 1, 1, 5, 3, 0 + 2), ("tc_odd_chunks", 1, 2, 300, 333, 2), ("tc_many_ctas", 5, 12, 1024, 1024, 2),
+    ("tc1_siglip_frame", 2, 12, 1024, 1024, 4), ("tc1_ragged", 2, 3, 130, 77, 4), ("tc1_odd_chunks", 1, 2, 300, 333, 4), ("clap", 2, 12, 77, 77, 1), ("clap_long", 1, 12, 300, 300, 1), ("pool", 3, 12, 1, 1024, 1),
     ("pool_blk", 3, 12, 1, 1024, 3), ("cls_blk", 2, 12, 1, 1569, 3), ("clap_blk_masked", 2, 3, 1, 77, 3)])
 def test_attention_d64_vs_fp32(name, B, H, Sq, Sk, impl):
     enc = load_pkg("encoders")
