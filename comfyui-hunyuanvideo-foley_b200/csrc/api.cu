@@ -37,7 +37,7 @@ extern "C" foley_status foley_gemm(const void* a, int32_t dtype, int64_t batch, 
     GemmLaunch L;
     L.a.ptr = a;
     L.a.dtype = dtype == FOLEY_DT_F32 ? DT_F32 : DT_BF16;     // fp16 shares the 16-bit operand layout and tensor maps
-    L.epi.f16 = dtype == FOLEY_DT_F16 ? 1 : 0;
+    L.f16 = dtype == FOLEY_DT_F16 ? 1 : 0;
     L.a.k = k; L.a.rows = rows; L.a.batch = batch; L.a.ld = lda; L.a.batch_stride = a_batch_stride;
     L.w = w; L.n = n;
     L.taps = taps; L.tap_off0 = tap_off0; L.tap_stride = tap_stride;

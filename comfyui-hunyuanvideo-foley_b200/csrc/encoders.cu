@@ -451,7 +451,7 @@ foley_status Encoder::gemm(cudaStream_t st, const bf16* A, long long rows, const
     int bn = 256;
     while (bn > 64 && mt * ((W.n + bn - 1) / bn) < num_sms) bn >>= 1;
     L.bn = bn;
-    L.epi.mode = EPI_BF16; L.epi.act = act; L.epi.out = out; L.epi.ldo = W.n; L.epi.bias = W.b; L.epi.f16 = f16;
+    L.epi.mode = EPI_BF16; L.epi.act = act; L.epi.out = out; L.epi.ldo = W.n; L.epi.bias = W.b; L.f16 = f16;
     L.epi.out_batch_stride = rows * W.n;
     std::string err;
     if (!launch_gemm(L, st, &err)) return fail(FOLEY_ERR_CUDA, err);
@@ -623,7 +623,9 @@ foley_status Encoder::clap_encode(const int32_t* ids, const int32_t* mask, int B
         EncLnArgs a1;                       // post-LN: x = LayerNorm(dense(attn) + x)
         a1.y = y; a1.res = x; a1.ln_w = w.ln1_w; a1.ln_b = w.ln1_b; a1.h_out = x; a1.rows = rows; a1.eps = cfg.layer_norm_eps;
         ST_OK(add_ln(st, a1));
-        ST_OK(gemm(st, x, rows, w.fc1, mlp, ACT_GELU_ERF));
+        ST_OK(gemm(st, x, rows, w.fc1, mlp, ACT_NONE));
+        FOLEY_CUDA_OK(launch_k(enc_gelu_erf_kernel, dim3(enc_blocks(rows * F / 8, 256)), dim3(256), 0, st, mlp, rows * F / 8));
+        ++launches;
         ST_OK(gemm(st, mlp, rows, w.fc2, y, ACT_NONE));
         EncLnArgs a2 = a1;
         a2.ln_w = w.ln2_w; a2.ln_b = w.ln2_b;

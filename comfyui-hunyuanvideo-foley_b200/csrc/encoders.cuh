@@ -132,6 +132,21 @@ __global__ void __launch_bounds__(256) enc_add_ln_kernel(const EncLnArgs a) {
     if (a.ln_w && a.h_out) enc_ln_row<NCH>(x, a.ln_w, a.ln_b, a.eps, a.h_out + row * C, lane);
 }
 
+// nn.GELU() (erf) in place on a bf16 tensor: the CLAP text tower's intermediate activation (2 x 77 rows; the bf16 GEMM
+// epilogues of the DiT step carry SiLU / GELU-tanh only, and are left exactly as they were).
+__global__ void enc_gelu_erf_kernel(__nv_bfloat16* __restrict__ x, long long n8) {
+    pdl_wait();
+    pdl_trigger();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    uint4* p = reinterpret_cast<uint4*>(x) + i;
+    float f[8];
+    unpack8(*p, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
+    *p = pack8(f);
+}
+
 // ------------------------------------------------------------------------------------------------ CLAP text embeddings
 // x = bf16(bf16(word[id] + type[0]) + pos[pos_id]); out = LayerNorm(x)   (HF ClapTextEmbeddings.forward, bf16 module)
 template <int NCH>

@@ -39,7 +39,7 @@ enum EpiMode : int {
     EPI_F32 = 2,     // out(fp32)[split] = acc     (raw partial sums; consumer applies bias/gate)
     EPI_DAC = 3,     // fp32 conv epilogue: y = acc + bias (+resid); out = y; out2 = snake(y) / tanh(y)
 };
-enum ActMode : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU_TANH = 2, ACT_TANH = 3, ACT_GELU_ERF = 4 };   // GELU_ERF: nn.GELU() of the CLAP text tower
+enum ActMode : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU_TANH = 2, ACT_TANH = 3, ACT_GELU_ERF = 4 };   // GELU_ERF (nn.GELU()): fp16 instantiations only
 
 struct GemmEpi {
     int mode = EPI_BF16;
@@ -48,9 +48,7 @@ struct GemmEpi {
     long long ldo = 0;              // elements between output rows
     long long out_batch_stride = 0; // elements between samples
     long long split_stride = 0;     // EPI_F32: elements between K-split partials
-    const void* bias = nullptr;     // bf16[N] (DiT; fp16[N] with f16) or fp32[ch_mod] (DAC); may be null
-    int f16 = 0;                    // EPI_BF16 only: operands, bias and output are IEEE fp16 instead of bf16 (same 16-bit layouts and
-                                    // tensor maps; kind::f16 instruction descriptor format 0) — the Synchformer runs under fp16 autocast
+    const void* bias = nullptr;     // bf16[N] (DiT; fp16[N] in the fp16 instantiations) or fp32[ch_mod] (DAC); may be null
     // --- EPI_DAC only
     void* out2 = nullptr;           // snake(y) with alpha (next conv's input); may be null
     const float* resid = nullptr;   // residual input, same indexing as out; may be null
@@ -106,12 +104,14 @@ __device__ __forceinline__ float apply_act(float x, int act) {
         case ACT_SILU: return x / (1.0f + expf(-x));
         case ACT_GELU_TANH: return gelu_tanh_f(x);
         case ACT_TANH: return tanhf(x);
-        case ACT_GELU_ERF: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
         default: return x;
     }
 }
 
-template <int BN, bool kTF32, bool kPair = false>
+// kF16: the 16-bit operands, the bias and the output are IEEE fp16 instead of bf16 (EPI_BF16 mode only; a separate
+// instantiation so that the bf16 kernels of the DiT step compile to exactly the code they had before the mode existed:
+// as a run-time flag it cost the step 1.3 %).
+template <int BN, bool kTF32, bool kPair = false, bool kF16 = false>
 __global__ void __launch_bounds__((GemmCfg<BN, kTF32, kPair>::THREADS), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const __grid_constant__ CUtensorMap tm_c, const GemmArgs g) {
@@ -305,7 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             }
         }
         if (lane == 0 && leader) {
-            const uint32_t idesc = make_idesc(kTF32 ? 2 : (g.epi.f16 ? 0 : 1), kPair ? 2 * Cfg::BM : Cfg::BM, BN);
+            constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : (kF16 ? 0 : 1), kPair ? 2 * Cfg::BM : Cfg::BM, BN);
             int s = -1;
             uint32_t ph = 1;
             for (int i = 0; i < num_kb; ++i) {
@@ -372,8 +372,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                         if (e.bias) bv = reinterpret_cast<const float*>(e.bias)[ch];
                         if (e.alpha) { al = e.alpha[ch]; ial = 1.0f / (al + 1e-9f); }
                     } else if (e.bias) {
-                        bv = e.f16 ? __half2float(reinterpret_cast<const __half*>(e.bias)[col])
-                                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.bias)[col]);
+                        if constexpr (kF16) bv = __half2float(reinterpret_cast<const __half*>(e.bias)[col]);
+                        else bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.bias)[col]);
                     }
                 }
                 epi_f[c] = bv; epi_f[256 + c] = al; epi_f[512 + c] = ial;
@@ -435,7 +435,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     a[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + __uint_as_float(b2);
                     a[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + __uint_as_float(b3);
                 }
-                if (e.f16) {      // fp16 module (Synchformer under autocast): nn.GELU() or no activation
+                if constexpr (kF16) {      // fp16 module (Synchformer under autocast): nn.GELU() or no activation
                     if (e.act == ACT_GELU_ERF) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) { const float x = f16_round(a[j]); a[j] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -455,9 +455,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 } else if (e.act == ACT_GELU_TANH) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) a[j] = gelu_tanh_f(bf16_round(a[j]));
-                } else if (e.act == ACT_GELU_ERF) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { const float x = bf16_round(a[j]); a[j] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
                 } else if (e.act != ACT_NONE) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) a[j] = apply_act(bf16_round(a[j]), e.act);

@@ -197,15 +197,17 @@ struct GemmLaunch {
     int prefetch_b = -1;       // -1: default distance
     int pair = -1;             // CTA-pair (cta_group::2) tiles: -1 default policy, 0 off, 1 on when the shape allows
     int cluster_m = -1;        // weight-tile multicast across this many consecutive m-tiles: -1 default policy, 1 off, 2 / 4
+    int f16 = 0;               // EPI_BF16 only: operands, bias and output are IEEE fp16 instead of bf16 (same 16-bit layouts and tensor
+                               // maps; kind::f16 instruction-descriptor format 0): the Synchformer runs under fp16 autocast
     long long out_rows = 0;    // output rows per sample (0 -> a.rows); may exceed a.rows (halo rows read as zero)
     GemmEpi epi;
 };
 
-template <int BN, bool kTF32, bool kPair = false>
+template <int BN, bool kTF32, bool kPair = false, bool kF16 = false>
 inline cudaError_t launch_gemm_inst(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
                                     const GemmArgs& args, dim3 grid, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, kTF32, kPair>;
-    auto kern = gemm_tcgen05_kernel<BN, kTF32, kPair>;
+    auto kern = gemm_tcgen05_kernel<BN, kTF32, kPair, kF16>;
     const int cx = kPair ? 2 : (args.cluster_m > 1 ? args.cluster_m : 1), cy = 1;
     static bool attr_set = false;
     if (!attr_set) {
@@ -248,7 +250,11 @@ inline bool gemm_init_attributes(std::string* err) {
     auto set = [&](auto kern, int bytes) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     };
-    set(gemm_persistent_kernel, PersistCfg::SMEM_BYTES);
+    set(gemm_persistent_kernel<false>, PersistCfg::SMEM_BYTES);
+    set(gemm_persistent_kernel<true>, PersistCfg::SMEM_BYTES);
+    set(gemm_tcgen05_kernel<64, false, false, true>, GemmCfg<64, false>::SMEM_BYTES);
+    set(gemm_tcgen05_kernel<128, false, false, true>, GemmCfg<128, false>::SMEM_BYTES);
+    set(gemm_tcgen05_kernel<256, false, false, true>, GemmCfg<256, false>::SMEM_BYTES);
     set(gemm_tcgen05_kernel<64, false>, GemmCfg<64, false>::SMEM_BYTES);
     set(gemm_tcgen05_kernel<128, false>, GemmCfg<128, false>::SMEM_BYTES);
     set(gemm_tcgen05_kernel<256, false>, GemmCfg<256, false>::SMEM_BYTES);
@@ -271,15 +277,16 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
     if (L.a.k % bk != 0) { if (err) *err = "GEMM K must be a multiple of the 128-byte k-block"; return false; }
     if (L.n % 16 != 0) { if (err) *err = "GEMM N must be a multiple of 16"; return false; }
     if (L.epi.mode == EPI_DAC && !tf32) { if (err) *err = "the DAC epilogue exists for fp32 / tf32 operands only"; return false; }
+    if (L.f16 && (tf32 || L.epi.mode != EPI_BF16)) { if (err) *err = "fp16 operands exist for the 16-bit output mode only"; return false; }
     const long long out_rows_c = L.out_rows > 0 ? L.out_rows : L.a.rows;
     const long long mt = ((out_rows_c + 127) / 128) * (L.a.batch > 0 ? L.a.batch : 1);
     const long long nt = (L.n + L.bn - 1) / L.bn;
     // CTA-pair (cta_group::2) tiles: need an even number of m-tiles and a 128/256-wide tile
     int pair = L.pair >= 0 ? L.pair : default_pair_mode();
-    if (mt % 2 != 0 || (L.bn != 256 && L.bn != 128) || (tf32 && L.bn != 256)) pair = 0;
+    if (mt % 2 != 0 || (L.bn != 256 && L.bn != 128) || (tf32 && L.bn != 256) || L.f16) pair = 0;
     // multicast clusters: cm consecutive m-tiles (grid.x) share every weight tile; bf16 single-CTA tiles only
     int cm = L.cluster_m > 0 ? L.cluster_m : default_mcast();
-    if (pair || tf32 || L.bn < 128) cm = 1;
+    if (pair || tf32 || L.bn < 128 || L.f16) cm = 1;
     while (cm > 1 && mt % cm != 0) cm >>= 1;
     {   // grids that go to the persistent kernel (below) keep whole-tile loads
         static int persist_env = -1;
@@ -345,7 +352,8 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
                 cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
                 cudaStreamIsCapturing(stream, &cs);
                 if (cs == cudaStreamCaptureStatusNone) {
-                    cudaFuncSetAttribute(gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfg::SMEM_BYTES);
+                    cudaFuncSetAttribute(gemm_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfg::SMEM_BYTES);
+                    cudaFuncSetAttribute(gemm_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfg::SMEM_BYTES);
                     p_attr = true;
                 }
             }
@@ -364,7 +372,8 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
             cfg.numAttrs = pdl_enabled() ? 1 : 0;
-            e = cudaLaunchKernelEx(&cfg, gemm_persistent_kernel, ma, mb, mc, args, pt);
+            e = L.f16 ? cudaLaunchKernelEx(&cfg, gemm_persistent_kernel<true>, ma, mb, mc, args, pt)
+                          : cudaLaunchKernelEx(&cfg, gemm_persistent_kernel<false>, ma, mb, mc, args, pt);
             if (e != cudaSuccess) {
                 if (err) *err = std::string("persistent GEMM launch failed: ") + cudaGetErrorString(e);
                 return false;
@@ -372,7 +381,12 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
             return true;
         }
     }
-    if (!tf32) {
+    if (!tf32 && L.f16) {          // fp16 operands (Synchformer): single-CTA tiles
+        if (L.bn == 64) e = launch_gemm_inst<64, false, false, true>(ma, mb, mc, args, grid, stream);
+        else if (L.bn == 128) e = launch_gemm_inst<128, false, false, true>(ma, mb, mc, args, grid, stream);
+        else if (L.bn == 256) e = launch_gemm_inst<256, false, false, true>(ma, mb, mc, args, grid, stream);
+        else { if (err) *err = "unsupported BN"; return false; }
+    } else if (!tf32) {
         if (L.bn == 64) e = launch_gemm_inst<64, false>(ma, mb, mc, args, grid, stream);
         else if (L.bn == 128) e = pair ? launch_gemm_inst<128, false, true>(ma, mb, mc, args, grid, stream)
                                        : launch_gemm_inst<128, false>(ma, mb, mc, args, grid, stream);

@@ -29,6 +29,7 @@ struct PersistTiles {
     int num_tiles;      // mb_total * n_tiles * splits
 };
 
+template <bool kF16 = false>      // fp16 operands / bias / output (see gemm.cuh): a separate instantiation
 __global__ void __launch_bounds__(PersistCfg::THREADS, 1)
 gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                        const __grid_constant__ CUtensorMap tm_c, const GemmArgs g, const PersistTiles pt) {
@@ -122,7 +123,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     } else if (warp == 1) {
         // ------------------------------------------------------------- MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(g.epi.f16 ? 0 : 1, Cfg::BM, Cfg::BN);
+            constexpr uint32_t idesc = make_idesc(kF16 ? 0 : 1, Cfg::BM, Cfg::BN);
             int s = 0;
             uint32_t ph = 0;
             int j = 0;   // local tile counter
@@ -202,7 +203,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                             float a[32];
 #pragma unroll
                             for (int jj = 0; jj < 32; ++jj) a[jj] = __uint_as_float(v[jj]);
-                            if (bias && e.f16) {
+                            if (bias && kF16) {
 #pragma unroll
                                 for (int jj = 0; jj < 4; ++jj) {
                                     const uint4 bw = __ldg(reinterpret_cast<const uint4*>(bias + n0 + c0) + jj);
@@ -225,7 +226,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                                     }
                                 }
                             }
-                            if (e.f16) {
+                            if constexpr (kF16) {
                                 if (e.act == ACT_GELU_ERF) {
 #pragma unroll
                                     for (int jj = 0; jj < 32; ++jj) { const float x = f16_round(a[jj]); a[jj] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -245,7 +246,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                             }
                             uint32_t packed[16];
 #pragma unroll
-                            for (int jj = 0; jj < 16; ++jj) packed[jj] = e.f16 ? pack_f16x2(a[2 * jj], a[2 * jj + 1]) : pack_bf16x2(a[2 * jj], a[2 * jj + 1]);
+                            for (int jj = 0; jj < 16; ++jj) packed[jj] = kF16 ? pack_f16x2(a[2 * jj], a[2 * jj + 1]) : pack_bf16x2(a[2 * jj], a[2 * jj + 1]);
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj)
                                 st_shared_v4(row_addr + (((piece0 + jj) ^ sw) << 4), packed[4 * jj], packed[4 * jj + 1],
