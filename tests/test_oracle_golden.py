@@ -120,3 +120,27 @@ def test_fp8_weight_storage_matches_reference_wrapper(golden_dir):
     # and FP8 storage is not a no-op: the plain fp32 golden differs at the percent level
     plain = torch.load(os.path.join(golden_dir, "dit_tiny_fp32.pt"))["out"]
     assert rel_l2(gold["out"], plain) > 1e-3
+
+
+def test_synchformer_golden_is_what_the_reference_module_computes(golden_dir):
+    """tests/golden/synchformer_d2.pt was written on a B200 by tools/gpu_synchformer_golden.py.  Here the reference's own
+    MotionFormer (models/synchformer/motionformer.py through the omegaconf / timm stand-ins of tools/ref_shims.py) is run
+    again on the CPU in fp32 with the same seeded weights and frames: it must reproduce the golden's fp32 output (1e-4: CPU
+    vs GPU fp32 summation order), which pins the weight / frame generators and the shims the GPU parity test relies on.
+    Skipped when no reference tree is available (the GPU box: the goldens are committed)."""
+    from tools import ref_shims as R
+    from tools import synthetic as SY
+    if not os.path.isdir(os.path.join(R.REF_ROOT, "hunyuanvideo_foley", "models", "synchformer")):
+        pytest.skip("no reference tree")
+    g = torch.load(os.path.join(golden_dir, "synchformer_d2.pt"))
+    model = R.load_motionformer(g["depth"])().eval()
+    model.load_state_dict(SY.synth_motionformer_state_dict(g["depth"], seed=g["weights_seed"]), strict=True)
+    frames = SY.synth_sync_frames(g["n_frames"], seed=g["frames_seed"])
+    S = (g["n_frames"] - 16) // 8 + 1
+    x = torch.stack([frames[i * 8: i * 8 + 16] for i in range(S)])[None].permute(0, 1, 3, 2, 4, 5)
+    with torch.inference_mode():
+        out = model(x)[0]
+    assert out.shape == g["out_fp32"].shape
+    assert rel_l2(out, g["out_fp32"]) < 1e-4
+    # and the autocast golden sits at the bf16-parameter / fp16-activation distance from it, not further
+    assert 1e-3 < rel_l2(g["out_autocast"], g["out_fp32"]) < 2e-2
