@@ -132,10 +132,14 @@ class Engine {
     bool att_fused = false;
     int side_split_cap = 0;              // > 0: cap on the K splits of the visual-branch GEMMs (FOLEY_SIDE_SPLITS): they run beside the
                                          // audio-stream GEMMs and every CTA they occupy is taken from those
-    bool mod_on_branch = false;          // measured: no gain (the GEMM saturates the SMs either way)
-    // planner cost model (us): a k-block costs the same for every tile width (one tcgen05.mma ~150 cycles whatever N), so
-    // wide tiles + more K-splits win whenever they fit the SMs (measured: tools/gemm_micro.py --dbg 4, FOLEY_PLAN sweeps)
-    double plan_tkb128 = 0.35, plan_tkb256 = 0.36, plan_tfix = 5.0, plan_tsplit = 0.4;
+    bool mod_on_branch = true;           // single-block modulation GEMM on its own graph branch under the triple-stream phase: no gain with
+                                         // the round-1 plans, 4.012 -> 3.991 ms with the plans below (profiles/r02_plan_sweep_*.log)
+    // planner cost model (us per k-block of a 128- / 256-wide tile, fixed cost per CTA wave, cost per extra K split).  Swept
+    // on the whole step at the end of round 2 (FOLEY_PLAN, profiles/r02_plan_sweep_*.log): pricing the 256-wide tile below the
+    // 128-wide one and a split at 0.85 us moves the visual-branch GEMMs (80 rows) from 128-wide tiles x 4 splits (132 CTAs)
+    // to 256-wide x 3 (51 CTAs) and the audio proj / cross-q GEMMs from 4 to 3 splits: the branch that runs BESIDE the audio
+    // stream takes fewer SMs from it.  Step 4.124 -> 4.012 ms on the same box.
+    double plan_tkb128 = 0.36, plan_tkb256 = 0.30, plan_tfix = 5.0, plan_tsplit = 0.85;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t own_stream = nullptr;   // blocking stream used when the caller passes NULL (legacy stream cannot be captured)
     // scratch of set_conditions / prepare_timesteps (plan-owned)
