@@ -5,6 +5,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -140,6 +141,11 @@ class Engine {
     // to 256-wide x 3 (51 CTAs) and the audio proj / cross-q GEMMs from 4 to 3 splits: the branch that runs BESIDE the audio
     // stream takes fewer SMs from it.  Step 4.124 -> 4.012 ms on the same box.
     double plan_tkb128 = 0.36, plan_tkb256 = 0.30, plan_tfix = 5.0, plan_tsplit = 0.85;
+    // per-shape overrides of the planner: (rows, batch, n, k-blocks) -> (tile width, K splits).  The built-in table below holds
+    // what tools/plan_search.py found on the whole step (coordinate descent, objective = measured ms per Euler step);
+    // FOLEY_PLAN_OVERRIDE="rows:batch:n:kb=bn:s;..." adds / replaces entries (the search tool drives it).
+    std::map<std::tuple<int, int, int, int>, std::pair<int, int>> plan_override;
+    mutable std::map<std::tuple<int, int, int, int>, std::pair<int, int>> plan_seen;   // every (shape -> plan) the planner returned
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t own_stream = nullptr;   // blocking stream used when the caller passes NULL (legacy stream cannot be captured)
     // scratch of set_conditions / prepare_timesteps (plan-owned)
