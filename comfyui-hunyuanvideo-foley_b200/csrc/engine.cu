@@ -848,6 +848,7 @@ foley_status Engine::step(cudaStream_t st) {
     // ---- single-block modulations for this step: x-independent, one GEMM for all NS blocks.  It only has to be ready
     // before the first single block, so it runs on its own graph branch underneath the triple-stream phase.
     const bool mod_branch = mod_on_branch && NT > 0;
+    bool mod_joined = false;
     cudaStream_t sm_ = mod_branch ? mod_stream : st;
     {
         if (mod_branch) {
@@ -1038,7 +1039,7 @@ foley_status Engine::step(cudaStream_t st) {
             ST_OK(proj_combine(sv, attn_out, Lv, B2, C, jb, w.cross_proj[1], part_v, cv));
         }
         // -- MLPs
-        if (mod_branch && i == NT - 1) FOLEY_CUDA_OK(cudaStreamWaitEvent(st, ev_mod, 0));   // next: LN-modulate with single-block params
+        if (mod_branch && i == NT - 1) { FOLEY_CUDA_OK(cudaStreamWaitEvent(st, ev_mod, 0)); mod_joined = true; }   // next: LN-modulate with single-block params
         ST_OK(gemm(st, h_a, L, B2, C, static_cast<long long>(L) * C, w.fc1[0], 0, F, bf(mlp_a, F, w.fc1[0].b, ACT_GELU_TANH), 1, pick_bn(L, B2, F, C / 64)));
         ST_OK(gemm(sv, h_v, RV, 1, C, 0, w.fc1[1], 0, F, bf(mlp_v, F, w.fc1[1].b, ACT_GELU_TANH), 1, 64));
         {
@@ -1056,6 +1057,7 @@ foley_status Engine::step(cudaStream_t st) {
         }
     }
     ST_OK(join());   // the side branch must be complete before the step (graph) ends
+    if (mod_branch && !mod_joined) FOLEY_CUDA_OK(cudaStreamWaitEvent(st, ev_mod, 0));   // (triple loop skipped by an ablation mask)
     // ---- single-stream blocks (hifi_foley.py:364-390)
     const long long sb = static_cast<long long>(L) * C, sh = static_cast<long long>(L) * 128;
     for (int j = 0; j < ((debug_skip >> 10) & 1 ? 0 : NS); ++j) {
