@@ -94,6 +94,7 @@ foley_status Engine::create(const foley_config* c, int dev) {
     FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_mod, cudaEventDisableTiming));
     FOLEY_CUDA_OK(cudaEventCreateWithFlags(&ev_null, cudaEventDisableTiming));
     if (const char* e = getenv("FOLEY_MOD_BRANCH")) mod_on_branch = atoi(e) != 0;
+    if (const char* e = getenv("FOLEY_MOD_CTAS")) mod_ctas = atoi(e);
     if (const char* e = getenv("FOLEY_QKV_SPLIT")) qkv_split = atoi(e) != 0;
     if (const char* e = getenv("FOLEY_PLAN")) sscanf(e, "%lf,%lf,%lf,%lf", &plan_tkb128, &plan_tkb256, &plan_tfix, &plan_tsplit);
     // plans found by tools/plan_search.py on the named configuration (xl, 5 s, batch 1: profiles/r02_plan_search_a.log): the
@@ -534,7 +535,7 @@ int Engine::pick_splits(int rows, int batch, int n, int kblocks, int bn) const {
 }
 
 foley_status Engine::gemm(cudaStream_t st, const bf16* A, int rows, int batch, long long lda, long long a_bs,
-                          const LinearW& W, int n_off, int n_cnt, GemmEpi epi, int splits, int bn) {
+                          const LinearW& W, int n_off, int n_cnt, GemmEpi epi, int splits, int bn, int max_ctas) {
     if (skip_gemm_once) { skip_gemm_once = false; return FOLEY_OK; }          // tools/ablate_step.py only
     if (debug_skip & (1 << 4)) { if (st == side_stream) return FOLEY_OK; }     // visual-branch GEMMs
     GemmLaunch Lc;
@@ -547,6 +548,7 @@ foley_status Engine::gemm(cudaStream_t st, const bf16* A, int rows, int batch, l
     Lc.tap_stride = 1;
     Lc.splits = splits;
     Lc.bn = bn;
+    Lc.max_ctas = max_ctas;
     if (epi.bias) epi.bias = reinterpret_cast<const bf16*>(epi.bias) + n_off;
     if (epi.out_batch_stride == 0) epi.out_batch_stride = static_cast<long long>(rows) * epi.ldo;
     Lc.epi = epi;
@@ -861,7 +863,7 @@ foley_status Engine::step(cudaStream_t st) {
         ++launches;
         skip_gemm_once = (debug_skip >> 3) & 1;
         ST_OK(gemm(sm_, vectok_act, G_eff * n_uq, 1, C, 0, mod_single_all, 0, NS * 6 * C,
-                   bf(mod_single, ms_tok, mod_single_all.b, 0), 1, 256));
+                   bf(mod_single, ms_tok, mod_single_all.b, 0), 1, 256, mod_branch ? mod_ctas : 0));
         if (mod_branch) FOLEY_CUDA_OK(cudaEventRecord(ev_mod, sm_));
     }
     // The visual stream (B2*Lv = 80 rows at 5 s) is pure launch/latency overhead next to the audio stream: run it on a

@@ -133,6 +133,9 @@ class Engine {
     bool att_fused = false;
     int side_split_cap = 0;              // > 0: cap on the K splits of the visual-branch GEMMs (FOLEY_SIDE_SPLITS): they run beside the
                                          // audio-stream GEMMs and every CTA they occupy is taken from those
+    int mod_ctas = 24;                   // grid cap of the (persistent) modulation GEMM when it runs on its branch (FOLEY_MOD_CTAS; 0 = all SMs):
+                                         // it has the whole triple-stream phase (1.4 ms) to finish, and every SM it holds is taken from the
+                                         // latency-critical kernels beside it: 148 CTAs 3.971 ms, 24 CTAs 3.932 ms (profiles/r02_mod_ctas_sweep.log)
     bool mod_on_branch = true;           // single-block modulation GEMM on its own graph branch under the triple-stream phase: no gain with
                                          // the round-1 plans, 4.012 -> 3.991 ms with the plans below (profiles/r02_plan_sweep_*.log)
     // planner cost model (us per k-block of a 128- / 256-wide tile, fixed cost per CTA wave, cost per extra K split).  Swept
@@ -196,7 +199,7 @@ class Engine {
     foley_status take_vec(const std::string& name, bf16** out, int64_t n_expected);
     foley_status raw_as_bf16(const std::string& name, bf16** out, RawTensor** rt);
     foley_status gemm(cudaStream_t st, const bf16* A, int rows, int batch, long long lda, long long a_bs,
-                      const LinearW& W, int n_off, int n_cnt, GemmEpi epi, int splits, int bn);
+                      const LinearW& W, int n_off, int n_cnt, GemmEpi epi, int splits, int bn, int max_ctas = 0);
     foley_status alloc_plan(int B, int U, int L, int Lv, int S, int T);
     void free_plan();
     void free_packed();

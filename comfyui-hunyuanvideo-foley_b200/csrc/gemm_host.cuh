@@ -197,6 +197,8 @@ struct GemmLaunch {
     int prefetch_b = -1;       // -1: default distance
     int pair = -1;             // CTA-pair (cta_group::2) tiles: -1 default policy, 0 off, 1 on when the shape allows
     int cluster_m = -1;        // weight-tile multicast across this many consecutive m-tiles: -1 default policy, 1 off, 2 / 4
+    int max_ctas = 0;          // persistent kernel only: cap on the grid (0 = one CTA per SM).  A GEMM that runs on a side branch of the
+                               // step graph under latency-critical kernels should not take every SM
     int f16 = 0;               // EPI_BF16 only: operands, bias and output are IEEE fp16 instead of bf16 (same 16-bit layouts and tensor
                                // maps; kind::f16 instruction-descriptor format 0): the Synchformer runs under fp16 autocast
     long long out_rows = 0;    // output rows per sample (0 -> a.rows); may exceed a.rows (halo rows read as zero)
@@ -363,7 +365,7 @@ inline bool launch_gemm(const GemmLaunch& L, cudaStream_t stream, std::string* e
             pt.n_tiles = static_cast<int>(grid.y);
             pt.num_tiles = static_cast<int>(tiles);
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(static_cast<unsigned>(std::min<long long>(tiles, sms)));
+            cfg.gridDim = dim3(static_cast<unsigned>(std::min<long long>(tiles, L.max_ctas > 0 ? std::min(L.max_ctas, sms) : sms)));
             cfg.blockDim = dim3(PersistCfg::THREADS);
             cfg.dynamicSmemBytes = PersistCfg::SMEM_BYTES;
             cfg.stream = stream;
