@@ -27,6 +27,10 @@
 //  TMA stores measured slower both in round 1 (+0.8 us) and with round 2's arrive-only barriers (w1|w3 29.8 vs 29.0 us), and
 //  so did keeping the next chunk's tcgen05.ld in flight (29.2 us, 168 registers): that epilogue is bound by its math — two
 //  MUFU ops and three bf16 roundings per output — not by its stores.)
+#ifndef FOLEY_PDL_EARLY_TRIGGER
+#define FOLEY_PDL_EARLY_TRIGGER 1   // griddepcontrol.launch_dependents right after this kernel's own dependency wait (0: after its mainloop): the next kernel
+                                    // becomes resident (prologue, weight prefetch) under this mainloop wherever resources allow: 3.937 -> 3.926 ms per step
+#endif
 #ifndef FOLEY_EPI_WARPS_BF16
 #define FOLEY_EPI_WARPS_BF16 8    // 16 measured: fc1 (GELU) 14.5 -> 13.7 us, but w2 / w1|w3 0.3 us slower; step 4.14 -> 4.17 ms
 #endif
@@ -381,10 +385,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         }
         pdl_wait();                          // outputs may alias buffers the predecessor still reads
+#if FOLEY_PDL_EARLY_TRIGGER
+        pdl_trigger();                       // as soon as this kernel runs: the next kernel becomes resident wherever resources allow
+#endif
         // (Parking these warps in a hardware barrier until warp 1 has seen the accumulator barrier, instead of letting
         // all of them poll it through the mainloop, measured no difference: try_wait suspends in hardware.)
         const bool acc_ok = mbar_wait(tmem_full_bar, 0, 0x300);
+#if !FOLEY_PDL_EARLY_TRIGGER
         pdl_trigger();                       // mainloop done: the next kernel may start its prologue
+#endif
         tc_fence_after();
         if (tprobe && threadIdx.x == 64) g_foley_times[5] = clock64();
         const bool row_ok = r < g.rows;
