@@ -368,7 +368,7 @@ def run_b200(args):
                 visual, text, args.duration, deps, cfg, guidance_scale=args.cfg, num_inference_steps=args.denoise_steps,
                 batch_size=B * world, sampler="euler", generator=g, batch_slice=(rank * B, (rank + 1) * B))
             full = par.gather_waveforms(audio.float(), B * world, dst=0)   # ONE gather of decoded waveforms
-            return full.cpu() if full is not None else None
+            return sampling.to_host(full) if full is not None else None
 
         for _ in range(max(1, args.warmup - 1)):
             e2e_once()

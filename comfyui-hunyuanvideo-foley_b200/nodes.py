@@ -415,7 +415,8 @@ class HunyuanFoleySampler:
             decoded_waveform, sample_rate = denoise_process_with_generator(
                 visual_feats, text_feats, audio_len_in_s, model_dict, hunyuan_cfg, guidance_scale=cfg_scale,
                 num_inference_steps=steps, batch_size=batch_size, sampler=sampler, generator=rng)
-        waveform_batch = decoded_waveform.float().cpu()
+        from .sampling import to_host
+        waveform_batch = to_host(decoded_waveform.float())
         audio_output_first = {"waveform": waveform_batch[0].unsqueeze(0), "sample_rate": sample_rate}
         audio_output_batch = {"waveform": waveform_batch, "sample_rate": sample_rate}
         return (audio_output_first, audio_output_batch)
