@@ -144,3 +144,69 @@ def test_synchformer_golden_is_what_the_reference_module_computes(golden_dir):
     assert rel_l2(out, g["out_fp32"]) < 1e-4
     # and the autocast golden sits at the bf16-parameter / fp16-activation distance from it, not further
     assert 1e-3 < rel_l2(g["out_autocast"], g["out_fp32"]) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ condition encoders (§8f row 1)
+def _perturbed(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() == 1 and "norm" in name.lower() and name.endswith("weight"):
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+            elif p.dim() == 1:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+            else:
+                p.add_(0.01 * torch.randn(p.shape, generator=g))
+    return model.eval()
+
+
+def test_siglip_oracle_matches_the_hf_module():
+    """oracle/encoders_oracle.py siglip_pooler_output against HF SiglipVisionModel (the module the reference calls through
+    get_image_features, feature_utils.py:71), seeded weights, CPU fp32."""
+    from transformers import SiglipVisionConfig, SiglipVisionModel
+    from oracle import encoders_oracle as EO
+    torch.manual_seed(1)
+    m = _perturbed(SiglipVisionModel(SiglipVisionConfig(hidden_size=768, intermediate_size=3072, num_hidden_layers=2, num_attention_heads=12,
+                                                        image_size=64, patch_size=16, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6)), 2)
+    px = torch.rand(3, 3, 64, 64, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    with torch.inference_mode():
+        want = m(pixel_values=px).pooler_output
+        got = EO.siglip_pooler_output({k: v for k, v in m.state_dict().items()}, px)
+    assert got.shape == want.shape == (3, 768)
+    assert rel_l2(got, want) < 1e-5
+
+
+def test_clap_oracle_matches_the_hf_module():
+    """clap_last_hidden_state against HF ClapTextModelWithProjection(...).last_hidden_state (feature_utils.py:134-137) with a
+    right-padded prompt pair and its attention mask; position-id rule included."""
+    from transformers import ClapTextConfig, ClapTextModelWithProjection
+    from oracle import encoders_oracle as EO
+    torch.manual_seed(4)
+    m = _perturbed(ClapTextModelWithProjection(ClapTextConfig(num_hidden_layers=2)), 5)
+    ids = torch.randint(3, 50265, (2, 11), generator=torch.Generator().manual_seed(6))
+    ids[:, 0] = 0
+    ids[0, 5] = 2
+    ids[0, 6:] = 1
+    ids[1, 10] = 2
+    mask = (ids != 1).long()
+    with torch.inference_mode():
+        want = m(input_ids=ids, attention_mask=mask).last_hidden_state
+        got = EO.clap_last_hidden_state({k: v for k, v in m.state_dict().items()}, ids, mask)
+    assert EO.clap_position_ids(ids)[0].tolist() == [2, 3, 4, 5, 6, 7, 1, 1, 1, 1, 1]
+    assert rel_l2(got, want) < 1e-5
+
+
+def test_synchformer_oracle_matches_the_reference_golden(golden_dir):
+    """synchformer_visual against the fp32 output of the reference's own MotionFormer (golden written on a B200 by
+    tools/gpu_synchformer_golden.py; reproduced on the CPU by the test above), same seeded weights and frames."""
+    from oracle import encoders_oracle as EO
+    from tools import synthetic as SY
+    g = torch.load(os.path.join(golden_dir, "synchformer_d2.pt"))
+    sd = SY.synth_motionformer_state_dict(g["depth"], seed=g["weights_seed"])
+    with torch.inference_mode():
+        got = EO.synchformer_visual(sd, SY.synth_sync_frames(g["n_frames"], seed=g["frames_seed"]))
+    want = g["out_fp32"].reshape(got.shape)
+    assert rel_l2(got, want) < 1e-4
+    # the Synchformer checkpoint's key names are accepted too
+    got2 = EO.synchformer_visual({"vfeat_extractor." + k: v for k, v in sd.items()}, SY.synth_sync_frames(g["n_frames"], seed=g["frames_seed"]))
+    assert torch.equal(got, got2)
